@@ -1,0 +1,188 @@
+"""Host-side mirror of the reference interface for the trace-loop path.
+
+Reference (Rust): ``scene::Parser::default().parse::<Box<Environment>>(json)`` (src/scene.rs:564,
+1466-1478) builds an ``Environment``; ``Environment::render(dimensions, time, threads, context)``
+(src/universe/mod.rs:300-357) renders one frame into a ``RawImage2d<u8>`` (RGB8, row 0 = bottom).
+The same names and argument meanings are kept here; the work is done by libeuclider_b200.so
+(C ABI in include/euclider_b200.h) on a B200.  There is no CPU rendering path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _capi
+from ._capi import (EuclCamera, EuclError, EuclFlatScene, EuclRenderOpts, EuclStats, EUCL_PIPELINE_MEGAKERNEL,
+                    EUCL_PIPELINE_WAVEFRONT, check, lib)
+
+ParserError = EuclError  # the reference's `ParserError` (src/scene.rs:524-552); see EuclError.status
+
+# `resources/universe_dim.jpg` (background of 3d_room / 3d_hallways) is absent from the reference
+# checkout (.MISSING_LARGE_BLOBS); the declared substitute is used by the library and the oracle alike.
+DEFAULT_TEXTURE_SUBSTITUTES = {"universe_dim.jpg": "universe_bright.jpg", "moon.jpg": "universe_bright.jpg"}
+
+
+@dataclass
+class SimulationContext:
+    """The fields of the reference's SimulationContext that `render` reads (src/simulation.rs:167-186)."""
+    resolution: int = 1  # the reference defaults to 8 (window / 8); headless renders use 1
+    debugging: bool = False
+
+
+@dataclass
+class RawImage2d:
+    """glium's RawImage2d<u8> as returned by Environment::render: RGB8, row 0 = bottom."""
+    data: np.ndarray  # uint8, shape (height, width, 3)
+    width: int
+    height: int
+    format: str = "U8U8U8"
+    hit_ids: Optional[np.ndarray] = None  # int32 (height, width): primary hit entity, -1 background, -2 checkerboard
+    stats: Optional[dict] = None
+
+    def to_top_down(self) -> np.ndarray:
+        return self.data[::-1]
+
+
+def _decode_image(path: Path) -> Tuple[int, int, bytes]:
+    """Decodes to RGBA8, row 0 = top -- the layout `image::DynamicImage::get_pixel` exposes
+    (alpha = 255 for RGB / L images, grey replicated)."""
+    from PIL import Image
+
+    with Image.open(path) as im:
+        rgba = im.convert("RGBA")
+        return rgba.width, rgba.height, rgba.tobytes()
+
+
+def stats_to_dict(st: EuclStats) -> dict:
+    levels = int(st.levels)
+    return {
+        "pixels": int(st.pixels), "segments": int(st.segments), "nodes": int(st.nodes),
+        "level_counts": [int(st.level_counts[i]) for i in range(levels)], "levels": levels,
+        "retries": int(st.retries), "launches": int(st.launches), "ms_total": float(st.ms_total),
+        "ms_raygen": float(st.ms_raygen), "ms_intersect": float(st.ms_intersect), "ms_shade": float(st.ms_shade),
+        "ms_resolve": float(st.ms_resolve),
+    }
+
+
+class Environment:
+    """A parsed universe (Universe3 / Universe4).  Mirrors `trait Environment` (src/universe/mod.rs:289-360)."""
+
+    def __init__(self, parsed_handle: int, texture_paths: Sequence[str]):
+        self._parsed = C.c_void_p(parsed_handle)
+        self._scenes: Dict[int, C.c_void_p] = {}
+        self.texture_paths = list(texture_paths)
+        flat = lib().eucl_parsed_flat(self._parsed)
+        self.camera: EuclCamera = flat.contents.camera.copy()  # pose the JSON constructs; mutable by the caller
+        self.pipeline = EUCL_PIPELINE_WAVEFRONT
+
+    # -- reference API ---------------------------------------------------------------------------
+    def max_depth(self) -> int:
+        return int(self.camera.max_depth)
+
+    def render(self, dimensions: Tuple[int, int], time: float = 0.0, threads: int = 0,
+               context: Optional[SimulationContext] = None, *, device: int = 0, want_hit_ids: bool = False,
+               band_rows: int = 0, band_rank: int = 0, band_world: int = 1, out: Optional[np.ndarray] = None) -> RawImage2d:
+        """Environment::render.  `time` is seconds since start (the reference passes a Duration);
+        `threads` is accepted for signature parity and ignored (the GPU schedules the pixels)."""
+        del threads
+        context = context or SimulationContext()
+        width, height = int(dimensions[0]) // context.resolution, int(dimensions[1]) // context.resolution
+        opts = EuclRenderOpts(width=width, height=height, time_seconds=float(time), band_rows=band_rows,
+                              band_rank=band_rank, band_world=band_world, pipeline=self.pipeline, compact_rows=0,
+                              want_hit_ids=int(want_hit_ids))
+        if out is None:
+            out = np.zeros((height, width, 3), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.size == height * width * 3 and out.flags["C_CONTIGUOUS"]
+        hit = np.full((height, width), -3, dtype=np.int32) if want_hit_ids else None
+        stats = EuclStats()
+        check(lib().eucl_render(self._device_scene(device), C.byref(self.camera), C.byref(opts), out.ctypes.data,
+                                hit.ctypes.data if hit is not None else None, C.byref(stats)))
+        return RawImage2d(out, width, height, hit_ids=hit, stats=stats_to_dict(stats))
+
+    # -- device-resident variant (inputs and outputs stay in HBM) --------------------------------
+    def render_device(self, d_out_rgb8: int, dimensions: Tuple[int, int], time: float = 0.0, *, device: int = 0,
+                      d_out_hit_ids: int = 0, band_rows: int = 0, band_rank: int = 0, band_world: int = 1,
+                      compact_rows: bool = False) -> dict:
+        width, height = int(dimensions[0]), int(dimensions[1])
+        opts = EuclRenderOpts(width=width, height=height, time_seconds=float(time), band_rows=band_rows,
+                              band_rank=band_rank, band_world=band_world, pipeline=self.pipeline,
+                              compact_rows=int(compact_rows), want_hit_ids=int(bool(d_out_hit_ids)))
+        stats = EuclStats()
+        check(lib().eucl_render_device(self._device_scene(device), C.byref(self.camera), C.byref(opts),
+                                       C.c_void_p(d_out_rgb8), C.c_void_p(d_out_hit_ids) if d_out_hit_ids else None,
+                                       C.byref(stats)))
+        return stats_to_dict(stats)
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    @property
+    def flat(self) -> EuclFlatScene:
+        return lib().eucl_parsed_flat(self._parsed).contents
+
+    @property
+    def dim(self) -> int:
+        return int(self.flat.dim)
+
+    def _device_scene(self, device: int) -> C.c_void_p:
+        if device not in self._scenes:
+            handle = C.c_void_p()
+            check(lib().eucl_scene_create(lib().eucl_parsed_flat(self._parsed), device, C.byref(handle)))
+            self._scenes[device] = handle
+        return self._scenes[device]
+
+    def close(self) -> None:
+        for handle in self._scenes.values():
+            lib().eucl_scene_destroy(handle)
+        self._scenes.clear()
+        if self._parsed:
+            lib().eucl_parsed_destroy(self._parsed)
+            self._parsed = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class Parser:
+    """scene::Parser (src/scene.rs:554-1478).  `resource_root` plays the role of the reference's
+    working directory for the `./resources/...` texture paths (src/scene.rs:1050-1072)."""
+    resource_root: Union[str, os.PathLike, None] = None
+    texture_substitutes: Dict[str, str] = field(default_factory=lambda: dict(DEFAULT_TEXTURE_SUBSTITUTES))
+
+    @classmethod
+    def default(cls, resource_root: Union[str, os.PathLike, None] = None) -> "Parser":
+        return cls(resource_root=resource_root)
+
+    def _resolve(self, texture_path: str) -> Path:
+        root = Path(self.resource_root) if self.resource_root is not None else Path.cwd()
+        p = root / texture_path
+        if not p.exists() and p.name in self.texture_substitutes:
+            p = p.with_name(self.texture_substitutes[p.name])
+        if not p.exists():
+            raise FileNotFoundError(f"texture `{texture_path}` not found under {root}")
+        return p
+
+    def parse(self, json_text: str, *, load_textures: bool = True) -> Environment:
+        handle = C.c_void_p()
+        check(lib().eucl_scene_parse(json_text.encode("utf-8"), C.byref(handle)))
+        n = lib().eucl_parsed_texture_count(handle)
+        paths = [lib().eucl_parsed_texture_path(handle, k).decode("utf-8") for k in range(n)]
+        if load_textures:
+            try:
+                for slot, tex in enumerate(paths):
+                    w, h, data = _decode_image(self._resolve(tex))
+                    check(lib().eucl_parsed_set_texture(handle, slot, w, h, data))
+            except Exception:
+                lib().eucl_parsed_destroy(handle)
+                raise
+        return Environment(handle.value, paths)
+
+    def parse_file(self, path: Union[str, os.PathLike], **kw) -> Environment:
+        return self.parse(Path(path).read_text(), **kw)

@@ -1,0 +1,1340 @@
+// oracle.cc -- CPU restatement of euclider's per-pixel trace loop.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product path (euclider_b200/, include/) may import,
+// link or execute this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// `--impl reference` legs do, and only as the checker / the CPU number.
+//
+// It follows the reference (Limeth/euclider, Rust, CPU-only) function by function, keeping the
+// recursive shape of the original -- recursion for the ray tree, lazily pulled + cached streams
+// for CSG -- which is deliberately NOT how the CUDA pipeline is organised (wavefront, eager CSG
+// lists), so the two are independent statements of the same semantics.  All arithmetic is f64 in
+// the reference's operation order; build with -ffp-contract=off (see Makefile).
+//
+// PARITY PINNING: the reference cannot be compiled here (no rustc/cargo, 20+ crates absent), so
+// this oracle is pinned by (1) the reference's own known-answer tests for this path
+// (shape.rs:1048-1148, util.rs:947-969,1007-1037; see tests/test_oracle_kats.py) and (2) code
+// reading.  Behaviour that lives in un-vendored crates (palette 0.2.1, noise 0.4.1, nalgebra
+// 0.8.2, json 0.11.13, meval 0.1.0, image 0.18) is "parity unpinned"; every such assumption is
+// listed in oracle/ASSUMPTIONS.md.
+//
+// Citations are relative to /root/reference/src/.
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+#include "euclider_b200.h"
+
+namespace {
+
+constexpr double PI = 3.14159265358979323846264338327950288;     // BaseFloat::pi()
+constexpr double FRAC_PI_2 = 1.57079632679489661923132169163975144; // BaseFloat::frac_pi_2()
+constexpr double APPROX_EPSILON = 1.0e-6; // nalgebra 0.8.2 ApproxEq::approx_epsilon (RECOLLECTION)
+
+// ---------------------------------------------------------------------------------------------
+// nalgebra 0.8 vector semantics: component-wise loops, dot = left-to-right sum in index order,
+// normalize = v / norm(v)
+template <int D>
+struct Vec {
+    double c[D];
+    double& operator[](int k) { return c[k]; }
+    double operator[](int k) const { return c[k]; }
+};
+template <int D>
+Vec<D> load(const double* p) {
+    Vec<D> r;
+    for (int k = 0; k < D; ++k) r[k] = p[k];
+    return r;
+}
+template <int D>
+Vec<D> operator+(const Vec<D>& a, const Vec<D>& b) {
+    Vec<D> r;
+    for (int k = 0; k < D; ++k) r[k] = a[k] + b[k];
+    return r;
+}
+template <int D>
+Vec<D> operator-(const Vec<D>& a, const Vec<D>& b) {
+    Vec<D> r;
+    for (int k = 0; k < D; ++k) r[k] = a[k] - b[k];
+    return r;
+}
+template <int D>
+Vec<D> operator-(const Vec<D>& a) {
+    Vec<D> r;
+    for (int k = 0; k < D; ++k) r[k] = -a[k];
+    return r;
+}
+template <int D>
+Vec<D> operator*(const Vec<D>& a, double s) {
+    Vec<D> r;
+    for (int k = 0; k < D; ++k) r[k] = a[k] * s;
+    return r;
+}
+template <int D>
+Vec<D> operator/(const Vec<D>& a, double s) {
+    Vec<D> r;
+    for (int k = 0; k < D; ++k) r[k] = a[k] / s;
+    return r;
+}
+template <int D>
+double dot(const Vec<D>& a, const Vec<D>& b) {
+    double s = a[0] * b[0];
+    for (int k = 1; k < D; ++k) s = s + a[k] * b[k];
+    return s;
+}
+template <int D>
+double norm_squared(const Vec<D>& a) { return dot(a, a); }
+template <int D>
+double norm(const Vec<D>& a) { return std::sqrt(norm_squared(a)); }
+template <int D>
+Vec<D> normalize(const Vec<D>& a) { return a / norm(a); }
+
+// util.rs:712-722
+template <int D>
+double angle_between(const Vec<D>& a, const Vec<D>& b) {
+    double result = std::acos(dot(a, b) / (norm(a) * norm(b)));
+    return std::isnan(result) ? 0.0 : result;
+}
+
+// Rust f64::signum
+double rust_signum(double x) {
+    if (std::isnan(x)) return x;
+    return std::signbit(x) ? -1.0 : 1.0;
+}
+// Rust f64::min / f64::max (ignore a NaN operand)
+double rust_min(double a, double b) { return std::fmin(a, b); }
+double rust_max(double a, double b) { return std::fmax(a, b); }
+
+// util.rs:287-299
+double remainder_f(double a, double b) {
+    double rem = std::fmod(a, b);
+    if (rem == 0.0) return 0.0;
+    if (a < 0.0) return b + rem;
+    return rem;
+}
+int64_t remainder_i(int64_t a, int64_t b) {
+    int64_t rem = a % b;
+    if (rem == 0) return 0;
+    if (a < 0) return b + rem;
+    return rem;
+}
+
+// ---------------------------------------------------------------------------------------------
+// palette 0.2.1 (RECOLLECTION): linear RGBA, no gamma on this path
+struct Rgba {
+    double r, g, b, a;
+};
+double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+struct Counters {
+    uint64_t nan_channel = 0; // App. A.6: NaN colour channel reaching to_pixel (reference panics)
+    uint64_t bad_texcoord = 0; // NaN / out-of-range texture index (reference panics)
+    uint64_t no_material = 0;  // material_at None on an exiting transmit (reference may panic)
+    uint64_t csg_runaway = 0;  // a CSG stream that never terminates (reference hangs)
+};
+
+uint8_t channel_to_u8(double c, Counters* cn) {
+    if (std::isnan(c)) { // reference: to_u8().unwrap() panics; defined here as 0 and counted
+        if (cn) cn->nan_channel++;
+        return 0;
+    }
+    return (uint8_t)(clamp01(c) * 255.0); // truncation
+}
+void to_pixel4(const Rgba& c, uint8_t out[4], Counters* cn) {
+    out[0] = channel_to_u8(c.r, cn);
+    out[1] = channel_to_u8(c.g, cn);
+    out[2] = channel_to_u8(c.b, cn);
+    out[3] = channel_to_u8(c.a, cn);
+}
+Rgba new_u8(const uint8_t p[4]) {
+    return Rgba{(double)p[0] / 255.0, (double)p[1] / 255.0, (double)p[2] / 255.0, (double)p[3] / 255.0};
+}
+struct Pre { // PreAlpha<Rgb>
+    double r, g, b, a;
+};
+Pre into_premultiplied(const Rgba& c) {
+    double a = clamp01(c.a);
+    return Pre{c.r * a, c.g * a, c.b * a, a};
+}
+Rgba from_premultiplied(const Pre& p) {
+    double a = clamp01(p.a);
+    if (std::isnormal(a)) return Rgba{p.r / a, p.g / a, p.b / a, a};
+    return Rgba{0.0, 0.0, 0.0, a};
+}
+
+// Blend on premultiplied colours: `s` is self (source), `d` the argument (destination).
+// darken / difference / over are what the benchmark scenes use; the rest follow the W3C
+// compositing formulas palette implements.
+Pre blend_pre(int fn, const Pre& s, const Pre& d) {
+    const double sa = s.a, da = d.a;
+    double alpha = clamp01(sa + da - sa * da);
+    auto each = [&](double a, double b) -> double {
+        switch (fn) {
+        case EUCL_BLEND_OVER: return a + b * (1.0 - sa);
+        case EUCL_BLEND_INSIDE: return a * da;
+        case EUCL_BLEND_OUTSIDE: return a * (1.0 - da);
+        case EUCL_BLEND_ATOP: return a * da + b * (1.0 - sa);
+        case EUCL_BLEND_XOR: return a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_PLUS: return a + b;
+        case EUCL_BLEND_MULTIPLY: return a * b + a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_SCREEN: return a + b - a * b;
+        case EUCL_BLEND_OVERLAY:
+            if (b * 2.0 <= da) return 2.0 * a * b + a * (1.0 - da) + b * (1.0 - sa);
+            return a * (1.0 + da) + b * (1.0 + sa) - 2.0 * a * b - da * sa;
+        case EUCL_BLEND_DARKEN: return rust_min(a * da, b * sa) + a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_LIGHTEN: return rust_max(a * da, b * sa) + a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_DODGE:
+            if (a == sa && !std::isnormal(b)) return a * (1.0 - da);
+            if (a == sa) return sa * da + a * (1.0 - da) + b * (1.0 - sa);
+            return sa * da * rust_min(1.0, (b / da) * sa / (sa - a)) + a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_BURN:
+            if (!std::isnormal(a) && b == da) return sa * da + b * (1.0 - sa);
+            if (!std::isnormal(a)) return b * (1.0 - sa);
+            return sa * da * (1.0 - rust_min(1.0, (1.0 - b / da) * sa / a)) + a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_HARD_LIGHT:
+            if (a * 2.0 <= sa) return 2.0 * a * b + a * (1.0 - da) + b * (1.0 - sa);
+            return a * (1.0 + da) + b * (1.0 + sa) - 2.0 * a * b - da * sa;
+        case EUCL_BLEND_SOFT_LIGHT: {
+            double m = std::isnormal(da) ? b / da : 0.0;
+            if (a * 2.0 <= sa) return b * (sa + (2.0 * a - sa) * (1.0 - m)) + a * (1.0 - da) + b * (1.0 - sa);
+            if (b * 4.0 <= da) {
+                double m2 = m * m, m3 = m2 * m;
+                return da * (2.0 * a - sa) * (m3 * 16.0 - m2 * 12.0 - m * 3.0) + a - a * da + b;
+            }
+            return da * (2.0 * a - sa) * (std::sqrt(m) - m) + a - a * da + b;
+        }
+        case EUCL_BLEND_DIFFERENCE: return a + b - 2.0 * rust_min(a * da, b * sa);
+        case EUCL_BLEND_EXCLUSION: return a + b - 2.0 * a * b;
+        }
+        return a;
+    };
+    switch (fn) {
+    case EUCL_BLEND_INSIDE: alpha = clamp01(sa * da); break;
+    case EUCL_BLEND_OUTSIDE: alpha = clamp01(sa * (1.0 - da)); break;
+    case EUCL_BLEND_ATOP: alpha = clamp01(da); break;
+    case EUCL_BLEND_XOR: alpha = clamp01(sa + da - 2.0 * sa * da); break;
+    case EUCL_BLEND_PLUS: alpha = clamp01(sa + da); break;
+    default: break;
+    }
+    return Pre{each(s.r, d.r), each(s.g, d.g), each(s.b, d.b), alpha};
+}
+
+// util.rs:265-285
+Rgba combine_palette_color(const Rgba& a, const Rgba& b, double a_ratio) {
+    if (a_ratio <= 0.0) return b;
+    if (a_ratio >= 1.0) return a;
+    return Rgba{a.r * a_ratio + b.r * (1.0 - a_ratio), a.g * a_ratio + b.g * (1.0 - a_ratio),
+                a.b * a_ratio + b.b * (1.0 - a_ratio), a.a * a_ratio + b.a * (1.0 - a_ratio)};
+}
+
+// surface.rs:295-390: blend_function_ratio is combine_palette_color, the named ones go through
+// premultiplied alpha
+Rgba blend_rgba(int fn, double ratio, const Rgba& source, const Rgba& destination) {
+    if (fn == EUCL_BLEND_RATIO) return combine_palette_color(source, destination, ratio);
+    return from_premultiplied(blend_pre(fn, into_premultiplied(source), into_premultiplied(destination)));
+}
+
+// palette Hsv -> Rgb, hue in degrees
+void hsv_to_rgb(double hue_degrees, double saturation, double value, double rgb[3]) {
+    double deg = hue_degrees;
+    if (std::isfinite(deg)) {
+        while (deg >= 360.0) deg = deg - 360.0;
+        while (deg < 0.0) deg = deg + 360.0;
+    }
+    double c = value * saturation;
+    double h = deg / 60.0;
+    double x = c * (1.0 - std::fabs(std::fmod(h, 2.0) - 1.0));
+    double m = value - c;
+    double r, g, b;
+    if (h >= 0.0 && h < 1.0) { r = c; g = x; b = 0.0; }
+    else if (h >= 1.0 && h < 2.0) { r = x; g = c; b = 0.0; }
+    else if (h >= 2.0 && h < 3.0) { r = 0.0; g = c; b = x; }
+    else if (h >= 3.0 && h < 4.0) { r = 0.0; g = x; b = c; }
+    else if (h >= 4.0 && h < 5.0) { r = x; g = 0.0; b = c; }
+    else { r = c; g = 0.0; b = x; }
+    rgb[0] = r + m;
+    rgb[1] = g + m;
+    rgb[2] = b + m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// noise 0.4.1 Perlin, 4-D (RECOLLECTION; see ASSUMPTIONS.md)
+void perlin_grad4(unsigned index, double g[4]) {
+    const double diag = 0.577350269189625764077083524672081875;
+    unsigned i = index % 32;
+    unsigned zero_at = i / 8, signs = i % 8;
+    int bit = 0;
+    for (unsigned k = 0; k < 4; ++k) {
+        if (k == zero_at) {
+            g[k] = 0.0;
+        } else {
+            g[k] = (signs >> bit) & 1u ? -diag : diag;
+            ++bit;
+        }
+    }
+}
+double perlin4(const uint8_t perm[256], const double point[4]) {
+    double floored[4], near_d[4], far_d[4];
+    long near_c[4], far_c[4];
+    for (int k = 0; k < 4; ++k) {
+        floored[k] = std::floor(point[k]);
+        near_c[k] = (long)floored[k];
+        far_c[k] = near_c[k] + 1;
+        near_d[k] = point[k] - floored[k];
+        far_d[k] = near_d[k] - 1.0;
+    }
+    double total = 0.0;
+    bool first = true;
+    // corner order f0000, f1000, f0100, f1100, ... (x fastest)
+    for (int corner = 0; corner < 16; ++corner) {
+        long c[4];
+        double d[4];
+        for (int k = 0; k < 4; ++k) {
+            bool far = (corner >> k) & 1;
+            c[k] = far ? far_c[k] : near_c[k];
+            d[k] = far ? far_d[k] : near_d[k];
+        }
+        double attn = 1.0 - (((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) + d[3] * d[3]);
+        double v = 0.0;
+        if (attn > 0.0) {
+            unsigned h = perm[(unsigned)(c[0] & 0xff)];
+            h = perm[h ^ (unsigned)(c[1] & 0xff)];
+            h = perm[h ^ (unsigned)(c[2] & 0xff)];
+            h = perm[h ^ (unsigned)(c[3] & 0xff)];
+            double g[4];
+            perlin_grad4(h, g);
+            double a2 = attn * attn;
+            v = (a2 * a2) * (((d[0] * g[0] + d[1] * g[1]) + d[2] * g[2]) + d[3] * g[3]);
+        }
+        if (first) {
+            total = v;
+            first = false;
+        } else {
+            total = total + v;
+        }
+    }
+    return total * 4.424369240215691;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene access
+
+template <int D>
+struct Hit { // shape.rs:88-109 (the `direction` copy is the ray direction; kept by the caller)
+    Vec<D> location;
+    Vec<D> normal;
+    double distance;
+};
+
+// --- primitives ------------------------------------------------------------------------
+// returns number of hits (0..2), sorted by distance
+template <int D>
+int intersect_prim(const EuclPrim& pr, const Vec<D>& location, const Vec<D>& direction, Hit<D> out[2]) {
+    switch (pr.kind) {
+    case EUCL_PRIM_VOID: return 0; // shape.rs:622-631
+    case EUCL_PRIM_SPHERE: { // shape.rs:652-731
+        Vec<D> center = load<D>(pr.v0);
+        double radius = pr.s0;
+        Vec<D> rel = location - center;
+        double a = norm_squared(direction);
+        double b = 2.0 * dot(direction, rel);
+        double c = norm_squared(rel) - radius * radius;
+        double d = b * b - 4.0 * a * c;
+        if (d < 0.0) return 0;
+        double d_sqrt = std::sqrt(d);
+        double t1 = (-b - d_sqrt) / (2.0 * a);
+        double t2 = (-b + d_sqrt) / (2.0 * a);
+        double t_first, t_second = 0.0;
+        bool has_first = false, has_second = false;
+        if (t1 >= 0.0) {
+            t_first = t1;
+            has_first = true;
+            if (t2 >= 0.0) {
+                t_second = t2;
+                has_second = true;
+            }
+        } else if (t2 >= 0.0) {
+            t_first = t2;
+            has_first = true;
+        }
+        if (!has_first) return 0;
+        out[0].location = location + direction * t_first;
+        out[0].normal = normalize(out[0].location - center);
+        out[0].distance = t_first;
+        if (!has_second) return 1;
+        out[1].location = location + direction * t_second;
+        out[1].normal = normalize(out[1].location - center);
+        out[1].distance = t_second;
+        return 2;
+    }
+    case EUCL_PRIM_HYPERPLANE:
+    case EUCL_PRIM_HALFSPACE: { // shape.rs:779-809, 843-870
+        Vec<D> n = load<D>(pr.v0);
+        double t = -(dot(n, location) + pr.s0) / dot(n, direction);
+        if (t < 0.0) return 0; // NaN and +inf pass, as in the reference
+        out[0].location = direction * t + location;
+        out[0].normal = n;
+        out[0].distance = t;
+        if (pr.kind == EUCL_PRIM_HALFSPACE) out[0].normal = out[0].normal * -pr.s1;
+        return 1;
+    }
+    case EUCL_PRIM_CYLINDER: { // shape.rs:935-1027
+        Vec<D> center = load<D>(pr.v0), axis = load<D>(pr.v1);
+        double radius = pr.s0;
+        Vec<D> a_vec = direction - axis * dot(direction, axis);
+        Vec<D> delta_location = location - center;
+        Vec<D> c_vec = delta_location - axis * dot(delta_location, axis);
+        double a = norm_squared(a_vec);
+        double b = (1.0 + 1.0) * dot(a_vec, c_vec);
+        double c = norm_squared(c_vec) - radius * radius;
+        double d = b * b - 4.0 * a * c;
+        if (d < 0.0) return 0;
+        double d_sqrt = std::sqrt(d);
+        double t1 = (-b - d_sqrt) / (2.0 * a);
+        double t2 = (-b + d_sqrt) / (2.0 * a);
+        double t_first, t_second = 0.0;
+        bool has_first = false, has_second = false;
+        if (t1 >= 0.0) {
+            t_first = t1;
+            has_first = true;
+            if (t2 >= 0.0) {
+                t_second = t2;
+                has_second = true;
+            }
+        } else if (t2 >= 0.0) {
+            t_first = t2;
+            has_first = true;
+        }
+        if (!has_first) return 0;
+        Vec<D> p1 = location + direction * t_first;
+        // get_closest_point_on_axis (shape.rs:929-932) of the FIRST hit, reused for the second
+        Vec<D> on_axis = axis * dot(axis, p1 - center) + center;
+        out[0].location = p1;
+        out[0].normal = normalize(p1 - on_axis);
+        out[0].distance = t_first;
+        if (!has_second) return 1;
+        Vec<D> p2 = location + direction * t_second;
+        out[1].location = p2;
+        out[1].normal = normalize(p2 - on_axis);
+        out[1].distance = t_second;
+        return 2;
+    }
+    }
+    return 0;
+}
+
+template <int D>
+bool prim_inside(const EuclPrim& pr, const Vec<D>& point) {
+    switch (pr.kind) {
+    case EUCL_PRIM_VOID: return true;       // shape.rs:614-619
+    case EUCL_PRIM_SPHERE: {                // shape.rs:734-738
+        Vec<D> center = load<D>(pr.v0);
+        return norm_squared(center - point) <= pr.s0 * pr.s0;
+    }
+    case EUCL_PRIM_HYPERPLANE: return false; // shape.rs:812-817
+    case EUCL_PRIM_HALFSPACE: {              // shape.rs:873-881
+        double result = dot(load<D>(pr.v0), point) + pr.s0;
+        return pr.s1 == rust_signum(result);
+    }
+    case EUCL_PRIM_CYLINDER: { // shape.rs:1030-1038
+        Vec<D> center = load<D>(pr.v0), axis = load<D>(pr.v1);
+        Vec<D> on_axis = axis * dot(axis, point - center) + center;
+        return norm_squared(point - on_axis) <= pr.s0 * pr.s0;
+    }
+    }
+    return false;
+}
+
+
+template <int D>
+struct Tracer {
+    const EuclFlatScene& s;
+    EuclCamera cam;
+    double time_seconds;
+    uint32_t max_depth;
+    Counters counters;
+    uint64_t level_counts[EUCL_MAX_LEVELS] = {0};
+
+    Tracer(const EuclFlatScene& scene, const EuclCamera& camera, double time)
+        : s(scene), cam(camera), time_seconds(time), max_depth(camera.max_depth) {}
+
+    // node helpers: post-order layout (include/euclider_b200.h)
+    int child_b(int n) const { return n - 1; }
+    int child_a(int n) const { return s.nodes[n - 1].first - 1; }
+
+    // shape.rs:587-601
+    bool node_inside(int n, const Vec<D>& point) const {
+        const EuclNode& nd = s.nodes[n];
+        switch (nd.op) {
+        case EUCL_CSG_LEAF: return prim_inside(s.prims[nd.prim], point);
+        case EUCL_CSG_UNION: return node_inside(child_a(n), point) || node_inside(child_b(n), point);
+        case EUCL_CSG_INTERSECTION: return node_inside(child_a(n), point) && node_inside(child_b(n), point);
+        case EUCL_CSG_COMPLEMENT: return node_inside(child_a(n), point) && !node_inside(child_b(n), point);
+        case EUCL_CSG_SYMDIFF: return node_inside(child_a(n), point) ^ node_inside(child_b(n), point);
+        }
+        return false;
+    }
+
+    // --- lazily pulled, cached CSG streams (util.rs:372-450 Provider; shape.rs:204-497) ------
+    struct Opt {
+        bool some;
+        Hit<D> hit;
+    };
+    struct NodeState {
+        std::vector<Opt> items; // Provider cache, including cached None entries
+        int index_a = 0, index_b = 0;
+        int leaf_count = -1, leaf_next = 0;
+        Hit<D> leaf_hits[2];
+    };
+    struct Streams {
+        const Tracer& tr;
+        int node_first;
+        Vec<D> location, direction;
+        std::vector<NodeState> st;
+        bool runaway = false;
+
+        Streams(const Tracer& t, int first, int root, const Vec<D>& loc, const Vec<D>& dir)
+            : tr(t), node_first(first), location(loc), direction(dir), st((size_t)(root - first + 1)) {}
+
+        // Provider::get (util.rs:395-419)
+        Opt get(int n, int index) {
+            NodeState& ns = st[(size_t)(n - node_first)];
+            while (index >= (int)ns.items.size()) {
+                if (ns.items.size() > 4096) { // the reference would never return
+                    runaway = true;
+                    return Opt{false, {}};
+                }
+                Opt item = next(n);
+                st[(size_t)(n - node_first)].items.push_back(item);
+            }
+            return st[(size_t)(n - node_first)].items[(size_t)index];
+        }
+
+        Opt next(int n) {
+            const EuclNode& nd = tr.s.nodes[n];
+            NodeState& ns = st[(size_t)(n - node_first)];
+            const Opt none{false, {}};
+            if (nd.op == EUCL_CSG_LEAF) {
+                if (ns.leaf_count < 0) ns.leaf_count = intersect_prim<D>(tr.s.prims[nd.prim], location, direction, ns.leaf_hits);
+                if (ns.leaf_next < ns.leaf_count) return Opt{true, ns.leaf_hits[ns.leaf_next++]};
+                ns.leaf_next++;
+                return none;
+            }
+            const int na = tr.child_a(n), nb = tr.child_b(n);
+            switch (nd.op) {
+            case EUCL_CSG_UNION: // shape.rs:212-264
+                for (;;) {
+                    if (runaway) return none;
+                    Opt a = get(na, ns.index_a), b = get(nb, ns.index_b);
+                    if (a.some) {
+                        if (b.some) {
+                            bool a_closer = a.hit.distance < b.hit.distance;
+                            const Hit<D>& closer = a_closer ? a.hit : b.hit;
+                            int further = a_closer ? nb : na;
+                            int& closer_index = a_closer ? ns.index_a : ns.index_b;
+                            if (!tr.node_inside(further, closer.location)) {
+                                closer_index += 1;
+                                return Opt{true, closer};
+                            }
+                            closer_index += 1;
+                        } else {
+                            ns.index_a += 1;
+                            if (tr.node_inside(nb, a.hit.location)) return none;
+                            return a;
+                        }
+                    } else {
+                        if (b.some) {
+                            ns.index_b += 1;
+                            if (tr.node_inside(na, b.hit.location)) return none;
+                        }
+                        return b;
+                    }
+                }
+            case EUCL_CSG_INTERSECTION: // shape.rs:291-340
+                for (;;) {
+                    if (runaway) return none;
+                    Opt a = get(na, ns.index_a), b = get(nb, ns.index_b);
+                    if (a.some) {
+                        if (b.some) {
+                            bool a_closer = a.hit.distance < b.hit.distance;
+                            const Hit<D>& closer = a_closer ? a.hit : b.hit;
+                            int further = a_closer ? nb : na;
+                            (a_closer ? ns.index_a : ns.index_b) += 1;
+                            if (tr.node_inside(further, closer.location)) return Opt{true, closer};
+                        } else {
+                            ns.index_a += 1;
+                            if (tr.node_inside(nb, a.hit.location)) return a;
+                            return none;
+                        }
+                    } else {
+                        if (b.some) {
+                            ns.index_b += 1;
+                            if (tr.node_inside(na, b.hit.location)) return b;
+                        }
+                        return none;
+                    }
+                }
+            case EUCL_CSG_COMPLEMENT: // shape.rs:365-409
+                for (;;) {
+                    if (runaway) return none;
+                    Opt a = get(na, ns.index_a), b = get(nb, ns.index_b);
+                    if (a.some) {
+                        if (b.some) {
+                            if (a.hit.distance < b.hit.distance) {
+                                ns.index_a += 1;
+                                if (!tr.node_inside(nb, a.hit.location)) return a;
+                            } else {
+                                ns.index_b += 1;
+                                if (tr.node_inside(na, b.hit.location)) {
+                                    Opt inv = b;
+                                    inv.hit.normal = -inv.hit.normal;
+                                    return inv;
+                                }
+                            }
+                        } else {
+                            return a; // NOT advanced (reference quirk, shape.rs:392)
+                        }
+                    } else {
+                        if (b.some) {
+                            ns.index_b += 1;
+                            if (tr.node_inside(na, b.hit.location)) {
+                                Opt inv = b;
+                                inv.hit.normal = -inv.hit.normal;
+                                return inv;
+                            }
+                        }
+                        return none;
+                    }
+                }
+            case EUCL_CSG_SYMDIFF: { // shape.rs:436-496 (not a loop)
+                Opt a = get(na, ns.index_a), b = get(nb, ns.index_b);
+                if (a.some) {
+                    if (b.some) {
+                        bool a_closer = a.hit.distance < b.hit.distance;
+                        Opt closer = a_closer ? a : b;
+                        int further = a_closer ? nb : na;
+                        (a_closer ? ns.index_a : ns.index_b) += 1;
+                        if (tr.node_inside(further, closer.hit.location)) closer.hit.normal = -closer.hit.normal;
+                        return closer;
+                    }
+                    ns.index_a += 1;
+                    if (tr.node_inside(nb, a.hit.location)) a.hit.normal = -a.hit.normal;
+                    return a;
+                }
+                if (b.some) {
+                    ns.index_b += 1;
+                    if (tr.node_inside(na, b.hit.location)) b.hit.normal = -b.hit.normal;
+                }
+                return b;
+            }
+            }
+            return none;
+        }
+    };
+
+    // Universe::intersect + `provider.iter().next()` (mod.rs:61-83,110-112): first item only
+    bool first_intersection(const EuclEntity& e, const Vec<D>& location, const Vec<D>& direction, Hit<D>* out) {
+        if (e.node_first == e.node_root) { // plain primitive: no stream machinery needed
+            Hit<D> hits[2];
+            int n = intersect_prim(s.prims[s.nodes[e.node_root].prim], location, direction, hits);
+            if (n == 0) return false;
+            *out = hits[0];
+            return true;
+        }
+        Streams streams(*this, e.node_first, e.node_root, location, direction);
+        auto item = streams.get(e.node_root, 0);
+        if (streams.runaway) counters.csg_runaway++;
+        if (!item.some) return false;
+        *out = item.hit;
+        return true;
+    }
+
+    // all items of an entity's stream up to the first None (test hook)
+    int all_intersections(const EuclEntity& e, const Vec<D>& location, const Vec<D>& direction, int max_items,
+                          Hit<D>* out) {
+        Streams streams(*this, e.node_first, e.node_root, location, direction);
+        int n = 0;
+        while (n < max_items) {
+            auto item = streams.get(e.node_root, n);
+            if (!item.some || streams.runaway) break;
+            out[n++] = item.hit;
+        }
+        return n;
+    }
+
+    // --- materials (material.rs) ------------------------------------------------------------
+    double eval_expr(int first, int len, const double* vars) const {
+        double st[64];
+        int sp = 0;
+        for (int i = first; i < first + len; ++i) {
+            const EuclExprOp& o = s.expr_ops[i];
+            switch (o.op) {
+            case EUCL_EX_CONST: st[sp++] = o.value; break;
+            case EUCL_EX_VAR: st[sp++] = vars[o.arg]; break;
+            case EUCL_EX_NEG: st[sp - 1] = -st[sp - 1]; break;
+            case EUCL_EX_FUNC1: {
+                double x = st[sp - 1], r = x;
+                switch (o.arg) {
+                case EUCL_FN_SQRT: r = std::sqrt(x); break;
+                case EUCL_FN_ABS: r = std::fabs(x); break;
+                case EUCL_FN_EXP: r = std::exp(x); break;
+                case EUCL_FN_LN: r = std::log(x); break;
+                case EUCL_FN_SIN: r = std::sin(x); break;
+                case EUCL_FN_COS: r = std::cos(x); break;
+                case EUCL_FN_TAN: r = std::tan(x); break;
+                case EUCL_FN_ASIN: r = std::asin(x); break;
+                case EUCL_FN_ACOS: r = std::acos(x); break;
+                case EUCL_FN_ATAN: r = std::atan(x); break;
+                case EUCL_FN_SINH: r = std::sinh(x); break;
+                case EUCL_FN_COSH: r = std::cosh(x); break;
+                case EUCL_FN_TANH: r = std::tanh(x); break;
+                case EUCL_FN_FLOOR: r = std::floor(x); break;
+                case EUCL_FN_CEIL: r = std::ceil(x); break;
+                case EUCL_FN_ROUND: r = std::round(x); break;
+                case EUCL_FN_SIGNUM: r = rust_signum(x); break;
+                }
+                st[sp - 1] = r;
+                break;
+            }
+            default: {
+                double b = st[--sp], a = st[sp - 1], r = 0.0;
+                switch (o.op) {
+                case EUCL_EX_ADD: r = a + b; break;
+                case EUCL_EX_SUB: r = a - b; break;
+                case EUCL_EX_MUL: r = a * b; break;
+                case EUCL_EX_DIV: r = a / b; break;
+                case EUCL_EX_REM: r = std::fmod(a, b); break;
+                case EUCL_EX_POW: r = std::pow(a, b); break;
+                case EUCL_EX_FUNC2:
+                    if (o.arg == EUCL_FN_ATAN2) r = std::atan2(a, b);
+                    else if (o.arg == EUCL_FN_MAX) r = std::fmax(a, b);
+                    else r = std::fmin(a, b);
+                    break;
+                }
+                st[sp - 1] = r;
+            }
+            }
+        }
+        return sp > 0 ? st[sp - 1] : 0.0;
+    }
+    // ComponentTransformation::transform_with (material.rs:91-112): every component expression
+    // sees the SAME input vector
+    void apply_transform(const EuclTransform& t, bool inverse, Vec<D>& v) const {
+        double in[D];
+        for (int k = 0; k < D; ++k) in[k] = v[k];
+        for (int k = 0; k < D; ++k)
+            v[k] = inverse ? eval_expr(t.inv_first[k], t.inv_len[k], in) : eval_expr(t.fwd_first[k], t.fwd_len[k], in);
+    }
+    void material_enter(int entity, Vec<D>& direction) const { // material.rs:133-137,150-154
+        const EuclMaterial& m = s.materials[s.entities[entity].material];
+        if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
+        for (int k = 0; k < m.n_transforms; ++k) apply_transform(s.transforms[m.transform_first + k], false, direction);
+    }
+    void material_exit(int entity, Vec<D>& direction) const { // material.rs:139-142,156-162
+        const EuclMaterial& m = s.materials[s.entities[entity].material];
+        if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
+        for (int k = m.n_transforms - 1; k >= 0; --k) apply_transform(s.transforms[m.transform_first + k], true, direction);
+    }
+
+    // mod.rs:229-251
+    int material_at(const Vec<D>& location) const {
+        for (int e = 0; e < s.n_entities; ++e)
+            if (node_inside(s.entities[e].node_root, location)) return e;
+        return -1;
+    }
+
+    // --- textures (surface.rs:434-542, d3/entity/surface.rs:60-68, d4/entity/surface.rs:11-15)
+    Rgba texel(const EuclTexture& t, double xf, double yf) {
+        // `<u32 as NumCast>::from(f)`: Some(trunc) iff -1 < f < 2^32; the reference unwraps
+        int64_t x = 0, y = 0;
+        if (!(xf > -1.0 && xf < 4294967296.0) || !(yf > -1.0 && yf < 4294967296.0)) {
+            counters.bad_texcoord++;
+        } else {
+            x = (int64_t)xf;
+            y = (int64_t)yf;
+        }
+        if (x >= (int64_t)t.width || y >= (int64_t)t.height) { // image::get_pixel would panic
+            counters.bad_texcoord++;
+            x = 0;
+            y = 0;
+        }
+        const uint8_t* p = s.texels + t.texel_offset + 4 * ((size_t)y * t.width + (size_t)x);
+        return Rgba{(double)p[0], (double)p[1], (double)p[2], (double)p[3]};
+    }
+    Rgba sample_texture(const EuclMappedTexture& mt, double u, double v) {
+        const EuclTexture& t = s.textures[mt.texture];
+        double width = (double)t.width, height = (double)t.height;
+        if (mt.filter == EUCL_TEX_NEAREST) { // surface.rs:434-451
+            double x = std::floor(u * width), y = std::floor(v * height);
+            if (!(x > -1.0 && x < 4294967296.0) || !(y > -1.0 && y < 4294967296.0)) {
+                counters.bad_texcoord++;
+                x = 0.0;
+                y = 0.0;
+            }
+            int64_t xi = remainder_i((int64_t)x, (int64_t)t.width), yi = remainder_i((int64_t)y, (int64_t)t.height);
+            Rgba p = texel(t, (double)xi, (double)yi);
+            return Rgba{p.r / 255.0, p.g / 255.0, p.b / 255.0, p.a / 255.0};
+        }
+        // surface.rs:453-489
+        double x = u * width - 0.5, y = v * height - 0.5;
+        double offset_x = x - std::floor(x), offset_y = y - std::floor(y);
+        Rgba px[4];
+        const double ox[4] = {0.0, 1.0, 0.0, 1.0}, oy[4] = {0.0, 0.0, 1.0, 1.0};
+        for (int k = 0; k < 4; ++k) px[k] = texel(t, remainder_f(x + ox[k], width), remainder_f(y + oy[k], height));
+        auto mix = [&](double p0, double p1, double p2, double p3) {
+            return ((p0 * (1.0 - offset_x) + p1 * offset_x) * (1.0 - offset_y) +
+                    (p2 * (1.0 - offset_x) + p3 * offset_x) * offset_y) /
+                   255.0;
+        };
+        return Rgba{mix(px[0].r, px[1].r, px[2].r, px[3].r), mix(px[0].g, px[1].g, px[2].g, px[3].g),
+                    mix(px[0].b, px[1].b, px[2].b, px[3].b), mix(px[0].a, px[1].a, px[2].a, px[3].a)};
+    }
+    Rgba mapped_color(int mapped, const Vec<D>& point) {
+        if (mapped < 0) return Rgba{0.0, 0.0, 0.0, 0.0}; // MappedTextureTransparent
+        const EuclMappedTexture& mt = s.mapped_textures[mapped];
+        // uv_sphere on the first three components (uv_derank drops w first)
+        Vec<3> p;
+        for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
+        p = normalize(p);
+        double u = 0.5 + std::atan2(p[1], p[0]) / (2.0 * PI);
+        double v = 0.5 - std::asin(p[2]) / PI;
+        return sample_texture(mt, u, v);
+    }
+
+    // --- shading ------------------------------------------------------------------------------
+    struct Context { // TracingContext (shape.rs:111-123)
+        int origin_entity;
+        int hit_entity;
+        Vec<D> direction; // intersection.direction == the ray direction
+        Hit<D> hit;
+        Vec<D> normal_closer;
+        bool exiting;
+    };
+
+    // util.rs:631-666
+    Vec<D> general_rotation(const Vec<D>& self, const Vec<D>& other, double angle, const Vec<D>& v) const {
+        double original[D][D], result[D][D]; // [row][col]
+        for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) original[r][c] = r == c ? 1.0 : 0.0;
+        for (int r = 0; r < D; ++r) {
+            original[r][0] = self[r];
+            original[r][1] = other[r];
+        }
+        std::memcpy(result, original, sizeof result);
+        for (int i = 1; i < D; ++i) {
+            for (int j = 0; j < i; ++j) {
+                Vec<D> oc, rc;
+                for (int r = 0; r < D; ++r) {
+                    oc[r] = original[r][i];
+                    rc[r] = result[r][j];
+                }
+                Vec<D> upd = oc - rc * dot(rc, oc);
+                for (int r = 0; r < D; ++r) original[r][i] = upd[r];
+            }
+            Vec<D> col;
+            for (int r = 0; r < D; ++r) col[r] = original[r][i];
+            col = normalize(col);
+            for (int r = 0; r < D; ++r) result[r][i] = col[r];
+        }
+        double rot[D][D];
+        for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) rot[r][c] = r == c ? 1.0 : 0.0;
+        rot[0][0] = std::cos(angle);
+        rot[0][1] = -std::sin(angle);
+        rot[1][0] = std::sin(angle);
+        rot[1][1] = std::cos(angle);
+        // result * (rotation_matrix * result.transpose()); nalgebra accumulates from zero
+        double tmp[D][D], q[D][D];
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < D; ++k) acc = acc + rot[i][k] * result[j][k];
+                tmp[i][j] = acc;
+            }
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < D; ++k) acc = acc + result[i][k] * tmp[k][j];
+                q[i][j] = acc;
+            }
+        Vec<D> out;
+        for (int i = 0; i < D; ++i) {
+            double acc = 0.0;
+            for (int j = 0; j < D; ++j) acc = acc + v[j] * q[i][j];
+            out[i] = acc;
+        }
+        return out;
+    }
+
+    double reflection_ratio(const EuclSurface& sf, const Context& c) const {
+        if (sf.ratio_op == EUCL_RATIO_UNIFORM) return c.exiting ? 0.0 : sf.ratio_a; // surface.rs:201-211
+        // surface.rs:214-244
+        Vec<D> normal = -c.normal_closer;
+        double from_theta = angle_between(c.direction, normal);
+        double from_index = c.exiting ? sf.ratio_a : sf.ratio_b;
+        double to_index = c.exiting ? sf.ratio_b : sf.ratio_a;
+        double to_theta = std::asin((from_index / to_index) * std::sin(from_theta));
+        if (std::isnan(to_theta)) return 1.0;
+        double product_1_s = from_index * std::cos(from_theta);
+        double product_2_s = to_index * std::cos(to_theta);
+        double product_1_p = from_index * std::cos(to_theta);
+        double product_2_p = to_index * std::cos(from_theta);
+        double rs = (product_1_s - product_2_s) / (product_1_s + product_2_s);
+        double rp = (product_1_p - product_2_p) / (product_1_p + product_2_p);
+        double reflectance_s = rs * rs, reflectance_p = rp * rp;
+        return (reflectance_s + reflectance_p) / (1.0 + 1.0);
+    }
+    Vec<D> reflection_direction(const Context& c) const { // surface.rs:246-256
+        return c.normal_closer * -2.0 * dot(c.direction, c.normal_closer) + c.direction;
+    }
+    Vec<D> threshold_direction(const EuclSurface& sf, const Context& c) const {
+        if (sf.thr_op == EUCL_THR_IDENTITY) return c.direction; // surface.rs:259-266
+        // surface.rs:268-288
+        Vec<D> normal = -c.normal_closer;
+        double from_theta = angle_between(c.direction, normal);
+        double modifier = c.exiting ? sf.thr_a : 1.0 / sf.thr_a;
+        double to_theta = std::asin(modifier * std::sin(from_theta));
+        double angle_delta = to_theta - from_theta;
+        return general_rotation(normal, c.direction, angle_delta, c.direction);
+    }
+
+    Rgba surface_color(const EuclSurface& sf, const Context& c) {
+        Rgba stack[16];
+        int sp = 0;
+        for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
+            const EuclColorOp& op = s.color_ops[i];
+            switch (op.op) {
+            case EUCL_COL_UNIFORM: stack[sp++] = Rgba{op.f[0], op.f[1], op.f[2], op.f[3]}; break;
+            case EUCL_COL_ILLUM_GLOBAL: { // surface.rs:410-422
+                Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
+                double original_angle = angle_between(c.normal_closer, c.direction);
+                double angle = PI - original_angle;
+                double ratio = angle / FRAC_PI_2;
+                stack[sp++] = combine_palette_color(dark, light, ratio);
+                break;
+            }
+            case EUCL_COL_ILLUM_DIR: { // surface.rs:392-408
+                Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
+                Vec<D> light_direction = load<D>(&op.f[8]);
+                Vec<D> normal = c.hit.normal;
+                if (angle_between(c.direction, normal) > FRAC_PI_2) normal = -normal;
+                double angle = angle_between(normal, -light_direction);
+                double ratio = 1.0 - angle / PI;
+                stack[sp++] = combine_palette_color(dark, light, ratio);
+                break;
+            }
+            case EUCL_COL_PERLIN_HUE: { // d3/entity/surface.rs:22-40
+                // (time * 1000).as_secs() as f64 / 1000.0
+                double time_millis = std::floor(time_seconds * 1000.0) / 1000.0;
+                double size = op.f[0], speed = op.f[1];
+                double location[4] = {c.hit.location[0] / size, c.hit.location[1] / size, c.hit.location[2] / size,
+                                      time_millis * speed};
+                double value = perlin4(s.perlin_perm, location);
+                double rgb[3];
+                hsv_to_rgb(value * 360.0, 1.0, 1.0, rgb);
+                stack[sp++] = Rgba{rgb[0], rgb[1], rgb[2], 1.0};
+                break;
+            }
+            case EUCL_COL_TEXTURE: stack[sp++] = mapped_color(op.i0, c.hit.location); break; // surface.rs:536-542
+            case EUCL_COL_BLEND: { // surface.rs:295-307
+                Rgba destination = stack[--sp];
+                Rgba source = stack[--sp];
+                stack[sp++] = blend_rgba(op.i0, op.f[0], source, destination);
+                break;
+            }
+            }
+        }
+        return sp > 0 ? stack[sp - 1] : Rgba{0.0, 0.0, 0.0, 0.0};
+    }
+
+    // mod.rs:85-147
+    bool trace_closest(const Vec<D>& location, const Vec<D>& direction, Context* out) {
+        bool have = false;
+        double closest_distance = 0.0;
+        for (int e = 0; e < s.n_entities; ++e) {
+            const EuclEntity& ent = s.entities[e];
+            if (ent.surface < 0) continue; // the filter of mod.rs:158-160
+            Hit<D> hit;
+            if (!first_intersection(ent, location, direction, &hit)) continue;
+            bool exiting;
+            Vec<D> closer_normal;
+            if (angle_between(direction, hit.normal) < FRAC_PI_2) {
+                closer_normal = -hit.normal;
+                exiting = true;
+            } else {
+                closer_normal = hit.normal;
+                exiting = false;
+            }
+            if (!have || closest_distance > hit.distance) {
+                out->hit_entity = e;
+                out->direction = direction;
+                out->hit = hit;
+                out->normal_closer = closer_normal;
+                out->exiting = exiting;
+                closest_distance = hit.distance;
+                have = true;
+            }
+        }
+        return have;
+    }
+
+    // mod.rs:149-184 with ComposableSurface::get_color inlined (surface.rs:62-162)
+    Rgba trace(uint32_t depth, int belongs_to, const Vec<D>& location, const Vec<D>& direction, int* primary_hit) {
+        level_counts[max_depth - depth]++;
+        Context c;
+        c.origin_entity = belongs_to;
+        if (depth > 0 && trace_closest(location, direction, &c)) {
+            if (primary_hit) *primary_hit = c.hit_entity;
+            const EuclSurface& sf = s.surfaces[s.entities[c.hit_entity].surface];
+            double ratio = rust_max(rust_min(reflection_ratio(sf, c), 1.0), 0.0);
+            const Vec<D> offset = c.normal_closer; // used as (+-n * eps) * 128
+            // get_intersection_color
+            bool have_intersection = false;
+            Rgba intersection_color{0, 0, 0, 0};
+            if (!(ratio >= 1.0)) {
+                Rgba sc = surface_color(sf, c);
+                uint8_t data[4];
+                to_pixel4(sc, data, &counters);
+                if (data[3] == 255) {
+                    intersection_color = sc;
+                    have_intersection = true;
+                } else {
+                    Vec<D> transitioned = threshold_direction(sf, c);
+                    Vec<D> new_origin = c.hit.location + (-offset) * APPROX_EPSILON * 128.0;
+                    int destination = c.exiting ? material_at(new_origin) : c.hit_entity;
+                    if (destination >= 0) {
+                        material_exit(belongs_to, transitioned);
+                        material_enter(destination, transitioned);
+                        Rgba transition = trace(depth - 1, destination, new_origin, transitioned, nullptr);
+                        uint8_t tdata[4];
+                        to_pixel4(transition, tdata, &counters);
+                        intersection_color =
+                            from_premultiplied(blend_pre(EUCL_BLEND_OVER, into_premultiplied(new_u8(data)),
+                                                         into_premultiplied(new_u8(tdata))));
+                        have_intersection = true;
+                    }
+                }
+            }
+            // get_reflection_color
+            bool have_reflection = false;
+            Rgba reflection_color{0, 0, 0, 0};
+            if (!(ratio <= 0.0)) {
+                Vec<D> rd = reflection_direction(c);
+                Vec<D> new_origin = c.hit.location + offset * APPROX_EPSILON * 128.0;
+                reflection_color = trace(depth - 1, belongs_to, new_origin, rd, nullptr);
+                have_reflection = true;
+            }
+            if (!have_intersection) {
+                if (!have_reflection) { // reference: expect() panics; defined as transparent black
+                    counters.no_material++;
+                    return Rgba{0, 0, 0, 0};
+                }
+                return reflection_color;
+            }
+            if (!have_reflection) return intersection_color;
+            return combine_palette_color(reflection_color, intersection_color, ratio);
+        }
+        if (primary_hit) *primary_hit = -1;
+        return mapped_color(s.background, direction); // `direction.to_point()`
+    }
+
+    // camera (d3/entity/camera.rs:164-185,369-390; d4/entity/camera.rs:155-176)
+    Vec<D> ray_vector(int x, int y, int width, int height) const {
+        double rel_x = (double)(x - width / 2) + (double)(1 - width % 2) / 2.0;
+        double rel_y = (double)(y - height / 2) + (double)(1 - height % 2) / 2.0;
+        double w = (double)width, h = (double)height;
+        Vec<D> location = load<D>(cam.location), forward = load<D>(cam.forward), up = load<D>(cam.up), right;
+        if (D == 3) {
+            Vec<3> cr;
+            cr[0] = cam.forward[1] * cam.up[2] - cam.forward[2] * cam.up[1];
+            cr[1] = cam.forward[2] * cam.up[0] - cam.forward[0] * cam.up[2];
+            cr[2] = cam.forward[0] * cam.up[1] - cam.forward[1] * cam.up[0];
+            cr = normalize(cr);
+            for (int k = 0; k < 3; ++k) right[k] = cr[k];
+        } else {
+            right = -load<D>(cam.left);
+        }
+        double fov_rad = PI * (double)cam.fov_deg / 180.0;
+        double distance = std::sqrt(w * w + h * h) / (2.0 * std::tan(fov_rad / 2.0));
+        Vec<D> center = location + forward * distance;
+        Vec<D> screen_point = center + (up * rel_y) + (right * rel_x);
+        return normalize(screen_point - location);
+    }
+
+    // trace_screen_point + trace_unknown (mod.rs:253-271,371-397) + to_pixel (mod.rs:342)
+    void pixel(int x, int y, int width, int height, uint8_t rgb[3], int32_t* hit_id) {
+        Vec<D> point = load<D>(cam.location);
+        Vec<D> vector = ray_vector(x, y, width, height);
+        int belongs_to = material_at(point);
+        double r, g, b;
+        if (belongs_to >= 0) {
+            Vec<D> transitioned = vector;
+            material_enter(belongs_to, transitioned);
+            int primary = -1;
+            Rgba fg = trace(max_depth, belongs_to, point, transitioned, &primary);
+            if (hit_id) *hit_id = primary;
+            Pre over = blend_pre(EUCL_BLEND_OVER, into_premultiplied(fg), into_premultiplied(Rgba{1.0, 1.0, 1.0, 1.0}));
+            Rgba out = from_premultiplied(over);
+            r = out.r;
+            g = out.g;
+            b = out.b;
+        } else {
+            if (hit_id) *hit_id = -2;
+            if ((x / 8 + y / 8) % 2 == 0) {
+                r = g = b = 0.0;
+            } else {
+                r = 1.0;
+                g = 0.0;
+                b = 1.0;
+            }
+        }
+        rgb[0] = channel_to_u8(r, &counters);
+        rgb[1] = channel_to_u8(g, &counters);
+        rgb[2] = channel_to_u8(b, &counters);
+    }
+};
+
+template <int D>
+int render_impl(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t width, uint32_t height, double time,
+                uint32_t row_begin, uint32_t row_end, int threads, uint8_t* out_rgb, int32_t* out_hit, uint64_t* stats) {
+    if (threads < 1) threads = 1;
+    std::atomic<uint32_t> next_row{row_begin};
+    std::vector<Tracer<D>> tracers;
+    tracers.reserve((size_t)threads);
+    for (int t = 0; t < threads; ++t) tracers.emplace_back(*scene, *camera, time);
+    auto work = [&](int t) {
+        Tracer<D>& tr = tracers[(size_t)t];
+        for (;;) {
+            uint32_t y = next_row.fetch_add(1);
+            if (y >= row_end) break;
+            for (uint32_t x = 0; x < width; ++x) {
+                size_t idx = (size_t)(y - row_begin) * width + x;
+                tr.pixel((int)x, (int)y, (int)width, (int)height, out_rgb + 3 * idx, out_hit ? out_hit + idx : nullptr);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    if (stats) {
+        // stats[0] = segments, [1] = nodes, [2..5] = undefined-corner counters, [8 + l] = level l
+        std::memset(stats, 0, sizeof(uint64_t) * (8 + EUCL_MAX_LEVELS));
+        for (auto& tr : tracers) {
+            for (uint32_t l = 0; l <= camera->max_depth && l < EUCL_MAX_LEVELS; ++l) {
+                stats[8 + l] += tr.level_counts[l];
+                stats[1] += tr.level_counts[l];
+                if (l < camera->max_depth) stats[0] += tr.level_counts[l];
+            }
+            stats[2] += tr.counters.nan_channel;
+            stats[3] += tr.counters.bad_texcoord;
+            stats[4] += tr.counters.no_material;
+            stats[5] += tr.counters.csg_runaway;
+        }
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// Renders rows [row_begin, row_end) of a width x height frame (row 0 = bottom) into out_rgb
+// (3 bytes per pixel, rows packed from row_begin) -- Environment::render, mod.rs:300-357.
+int oracle_render(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t width, uint32_t height, double time,
+                  uint32_t row_begin, uint32_t row_end, int threads, uint8_t* out_rgb, int32_t* out_hit,
+                  uint64_t* stats) {
+    if (!scene || !camera || !out_rgb || camera->max_depth + 1 > EUCL_MAX_LEVELS) return -1;
+    if (scene->dim == 3)
+        return render_impl<3>(scene, camera, width, height, time, row_begin, row_end, threads, out_rgb, out_hit, stats);
+    if (scene->dim == 4)
+        return render_impl<4>(scene, camera, width, height, time, row_begin, row_end, threads, out_rgb, out_hit, stats);
+    return -1;
+}
+
+// --- unit-test hooks -------------------------------------------------------------------------
+
+// Full intersection stream of entity `entity` (up to the first None): out = n x (distance,
+// location[dim], normal[dim]).
+int oracle_entity_intersections(const EuclFlatScene* scene, int entity, const double* location, const double* direction,
+                                int max_items, double* out) {
+    EuclCamera cam{};
+    cam.max_depth = 1;
+    if (scene->dim == 3) {
+        Tracer<3> tr(*scene, cam, 0.0);
+        std::vector<Hit<3>> hits((size_t)max_items);
+        int n = tr.all_intersections(scene->entities[entity], load<3>(location), load<3>(direction), max_items, hits.data());
+        for (int i = 0; i < n; ++i) {
+            out[i * 7] = hits[(size_t)i].distance;
+            for (int k = 0; k < 3; ++k) {
+                out[i * 7 + 1 + k] = hits[(size_t)i].location[k];
+                out[i * 7 + 4 + k] = hits[(size_t)i].normal[k];
+            }
+        }
+        return n;
+    }
+    Tracer<4> tr(*scene, cam, 0.0);
+    std::vector<Hit<4>> hits((size_t)max_items);
+    int n = tr.all_intersections(scene->entities[entity], load<4>(location), load<4>(direction), max_items, hits.data());
+    for (int i = 0; i < n; ++i) {
+        out[i * 9] = hits[(size_t)i].distance;
+        for (int k = 0; k < 4; ++k) {
+            out[i * 9 + 1 + k] = hits[(size_t)i].location[k];
+            out[i * 9 + 5 + k] = hits[(size_t)i].normal[k];
+        }
+    }
+    return n;
+}
+
+// One primitive against one ray in 2, 3 or 4 dimensions (the reference's KATs are 2-D,
+// shape.rs:1048-1148): out = n x (distance, location[dim], normal[dim]); returns n.
+int oracle_prim_intersect(int dim, const EuclPrim* prim, const double* location, const double* direction, double* out) {
+    auto run = [&](auto tag) {
+        constexpr int D = decltype(tag)::value;
+        Hit<D> hits[2];
+        int n = intersect_prim<D>(*prim, load<D>(location), load<D>(direction), hits);
+        for (int i = 0; i < n; ++i) {
+            out[i * (1 + 2 * D)] = hits[i].distance;
+            for (int k = 0; k < D; ++k) {
+                out[i * (1 + 2 * D) + 1 + k] = hits[i].location[k];
+                out[i * (1 + 2 * D) + 1 + D + k] = hits[i].normal[k];
+            }
+        }
+        return n;
+    };
+    if (dim == 2) return run(std::integral_constant<int, 2>{});
+    if (dim == 3) return run(std::integral_constant<int, 3>{});
+    return run(std::integral_constant<int, 4>{});
+}
+int oracle_prim_inside(int dim, const EuclPrim* prim, const double* point) {
+    if (dim == 2) return prim_inside<2>(*prim, load<2>(point));
+    if (dim == 3) return prim_inside<3>(*prim, load<3>(point));
+    return prim_inside<4>(*prim, load<4>(point));
+}
+
+int oracle_entity_inside(const EuclFlatScene* scene, int entity, const double* point) {
+    EuclCamera cam{};
+    if (scene->dim == 3) return Tracer<3>(*scene, cam, 0.0).node_inside(scene->entities[entity].node_root, load<3>(point));
+    return Tracer<4>(*scene, cam, 0.0).node_inside(scene->entities[entity].node_root, load<4>(point));
+}
+
+int oracle_material_at(const EuclFlatScene* scene, const double* point) {
+    EuclCamera cam{};
+    if (scene->dim == 3) return Tracer<3>(*scene, cam, 0.0).material_at(load<3>(point));
+    return Tracer<4>(*scene, cam, 0.0).material_at(load<4>(point));
+}
+
+double oracle_angle_between(int dim, const double* a, const double* b) {
+    if (dim == 2) return angle_between(load<2>(a), load<2>(b));
+    if (dim == 3) return angle_between(load<3>(a), load<3>(b));
+    return angle_between(load<4>(a), load<4>(b));
+}
+// f32 variant of util.rs:712-722 for the reference's own f32 test (util.rs:1007-1037)
+float oracle_angle_between_f32(const float* a, const float* b) {
+    float d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    float na = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    float nb = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+    float r = std::acos(d / (na * nb));
+    return std::isnan(r) ? 0.0f : r;
+}
+
+void oracle_combine_palette_color(const double* a, const double* b, double ratio, double* out) {
+    Rgba r = combine_palette_color(Rgba{a[0], a[1], a[2], a[3]}, Rgba{b[0], b[1], b[2], b[3]}, ratio);
+    out[0] = r.r;
+    out[1] = r.g;
+    out[2] = r.b;
+    out[3] = r.a;
+}
+// f32 variant for the reference's own test (util.rs:947-958 runs with f32 literals)
+void oracle_combine_palette_color_f32(const float* a, const float* b, float ratio, float* out) {
+    for (int k = 0; k < 4; ++k) out[k] = ratio <= 0.0f ? b[k] : ratio >= 1.0f ? a[k] : a[k] * ratio + b[k] * (1.0f - ratio);
+}
+
+int64_t oracle_remainder_i(int64_t a, int64_t b) { return remainder_i(a, b); }
+double oracle_remainder_f(double a, double b) { return remainder_f(a, b); }
+
+void oracle_blend(int fn, double ratio, const double* src, const double* dst, double* out) {
+    Rgba r = blend_rgba(fn, ratio, Rgba{src[0], src[1], src[2], src[3]}, Rgba{dst[0], dst[1], dst[2], dst[3]});
+    out[0] = r.r;
+    out[1] = r.g;
+    out[2] = r.b;
+    out[3] = r.a;
+}
+
+void oracle_to_pixel(const double* rgba, uint8_t* out) {
+    to_pixel4(Rgba{rgba[0], rgba[1], rgba[2], rgba[3]}, out, nullptr);
+}
+
+double oracle_perlin4(const uint8_t* perm, const double* point) { return perlin4(perm, point); }
+
+void oracle_hsv_to_rgb(double h, double s, double v, double* rgb) { hsv_to_rgb(h, s, v, rgb); }
+
+void oracle_general_rotation(int dim, const double* self, const double* other, double angle, const double* v, double* out) {
+    EuclFlatScene dummy{};
+    EuclCamera cam{};
+    if (dim == 3) {
+        Vec<3> r = Tracer<3>(dummy, cam, 0.0).general_rotation(load<3>(self), load<3>(other), angle, load<3>(v));
+        for (int k = 0; k < 3; ++k) out[k] = r[k];
+    } else {
+        Vec<4> r = Tracer<4>(dummy, cam, 0.0).general_rotation(load<4>(self), load<4>(other), angle, load<4>(v));
+        for (int k = 0; k < 4; ++k) out[k] = r[k];
+    }
+}
+
+// reflection ratio / directions of surface `surface` for a synthetic hit
+void oracle_surface_probe(const EuclFlatScene* scene, int surface, const double* direction, const double* normal_closer,
+                          int exiting, double* ratio, double* reflect_dir, double* threshold_dir) {
+    EuclCamera cam{};
+    const EuclSurface& sf = scene->surfaces[surface];
+    if (scene->dim == 3) {
+        Tracer<3> tr(*scene, cam, 0.0);
+        Tracer<3>::Context c{};
+        c.direction = load<3>(direction);
+        c.normal_closer = load<3>(normal_closer);
+        c.exiting = exiting != 0;
+        *ratio = tr.reflection_ratio(sf, c);
+        Vec<3> r = tr.reflection_direction(c), t = tr.threshold_direction(sf, c);
+        for (int k = 0; k < 3; ++k) {
+            reflect_dir[k] = r[k];
+            threshold_dir[k] = t[k];
+        }
+    } else {
+        Tracer<4> tr(*scene, cam, 0.0);
+        Tracer<4>::Context c{};
+        c.direction = load<4>(direction);
+        c.normal_closer = load<4>(normal_closer);
+        c.exiting = exiting != 0;
+        *ratio = tr.reflection_ratio(sf, c);
+        Vec<4> r = tr.reflection_direction(c), t = tr.threshold_direction(sf, c);
+        for (int k = 0; k < 4; ++k) {
+            reflect_dir[k] = r[k];
+            threshold_dir[k] = t[k];
+        }
+    }
+}
+
+void oracle_mapped_color(const EuclFlatScene* scene, int mapped, const double* point, double* out) {
+    EuclCamera cam{};
+    Rgba r;
+    if (scene->dim == 3) r = Tracer<3>(*scene, cam, 0.0).mapped_color(mapped, load<3>(point));
+    else r = Tracer<4>(*scene, cam, 0.0).mapped_color(mapped, load<4>(point));
+    out[0] = r.r;
+    out[1] = r.g;
+    out[2] = r.b;
+    out[3] = r.a;
+}
+
+void oracle_ray_vector(const EuclFlatScene* scene, const EuclCamera* cam, int x, int y, int w, int h, double* out) {
+    if (scene->dim == 3) {
+        Vec<3> r = Tracer<3>(*scene, *cam, 0.0).ray_vector(x, y, w, h);
+        for (int k = 0; k < 3; ++k) out[k] = r[k];
+    } else {
+        Vec<4> r = Tracer<4>(*scene, *cam, 0.0).ray_vector(x, y, w, h);
+        for (int k = 0; k < 4; ++k) out[k] = r[k];
+    }
+}
+
+} // extern "C"
