@@ -23,8 +23,8 @@ GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the reference (Rust/LLVM) never contracts a*b+c; bit-matching its hit decisions
 # needs separate DMUL/DADD.  No fast-math anywhere.
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
-CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra"]
+              "-Xcompiler", "-fPIC,-Wall,-ffp-contract=off", "-Xptxas", "-v"]
+CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off"]
 
 
 def _sources():

@@ -1,14 +1,559 @@
-// temporary stub
-#include "euclider_b200.h"
+// Device half of the C ABI (include/euclider_b200.h): scene upload, frame orchestration, IPC.
+//
+// eucl_render* is the drop-in for Environment::render (src/universe/mod.rs:300-357): it fans the
+// pixels out to the GPU instead of a scoped thread pool and returns the same RGB8 buffer
+// (row 0 = bottom).  There is no CPU rendering path here: without a usable CUDA device every
+// entry point fails with EUCL_ERR_NO_DEVICE / EUCL_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
 #include "error.h"
-extern "C" {
-int eucl_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
-int eucl_scene_create(const EuclFlatScene*, int, EuclScene**) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
-void eucl_scene_destroy(EuclScene*) {}
-int eucl_render(EuclScene*, const EuclCamera*, const EuclRenderOpts*, uint8_t*, int32_t*, EuclStats*) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
-int eucl_render_device(EuclScene*, const EuclCamera*, const EuclRenderOpts*, void*, void*, EuclStats*) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
-int eucl_ipc_export(void*, uint8_t*) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
-int eucl_ipc_open(const uint8_t*, int, void**) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
-int eucl_ipc_close(void*) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
-int eucl_fp64_peak(int, double*, double*, double*) { return eucl::fail(EUCL_ERR_NO_DEVICE, "stub"); }
+#include "euclider_b200.h"
+#include "intersect.cuh"
+#include "pipeline.cuh"
+#include "scene_dev.cuh"
+
+namespace {
+
+using namespace eucl;
+
+#define EUCL_CUDA(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(_e == cudaErrorMemoryAllocation ? EUCL_ERR_OUT_OF_MEMORY : EUCL_ERR_CUDA,         \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                              \
+    } while (0)
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : fallback;
 }
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+} // namespace
+
+struct EuclScene {
+    int device = 0;
+    int dim = 3;
+    int sm_count = 148;
+    int blob_bytes = 0;
+    size_t smem_bytes = 0;
+    uint8_t* d_blob = nullptr;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> tex_objects;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // workspace (grow-only)
+    DeviceBuffer nodes;    // the node arena
+    DeviceBuffer small;    // counters
+    DeviceBuffer frame;    // device frame buffer for eucl_render (host output)
+    DeviceBuffer hit_ids;  // device hit-id map for eucl_render
+    int arena_capacity = 0;
+    double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
+    int32_t* h_small = nullptr; // pinned mirror of the counters
+};
+
+namespace {
+
+constexpr int kSmallInts = 4 * (EUCL_MAX_LEVELS + 1) + 16; // per chunk: count, level_off, flags
+struct SmallLayout {                                        // one per chunk, in ints
+    static constexpr int count = 0;
+    static constexpr int level_off = EUCL_MAX_LEVELS + 1;
+    static constexpr int overflow = 2 * (EUCL_MAX_LEVELS + 1);
+    static constexpr int cam_entity = overflow + 1;
+    static constexpr int undefined64 = overflow + 2;                  // 8-byte aligned (even index)
+    static constexpr int mega64 = undefined64 + 2;                    // (EUCL_MAX_LEVELS + 1) x u64
+    static constexpr int total = mega64 + 2 * (EUCL_MAX_LEVELS + 1);
+};
+static_assert(SmallLayout::undefined64 % 2 == 0, "u64 counters must be 8-byte aligned");
+static_assert(SmallLayout::total <= kSmallInts, "small buffer layout");
+
+size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+// Leaves / hits a CSG program can hold, to validate against the per-thread arena (intersect.cuh)
+int validate_programs(const EuclFlatScene& f, std::string* why) {
+    for (int e = 0; e < f.n_entities; ++e) {
+        const EuclEntity& ent = f.entities[e];
+        if (ent.node_first < 0 || ent.node_root >= f.n_nodes || ent.node_first > ent.node_root) {
+            *why = "entity " + std::to_string(e) + ": node range out of bounds";
+            return EUCL_ERR_INVALID_ARGUMENT;
+        }
+        int leaf_hits = 0, depth = 0, max_depth = 0;
+        for (int n = ent.node_first; n <= ent.node_root; ++n) {
+            const EuclNode& nd = f.nodes[n];
+            if (nd.op == EUCL_CSG_LEAF) {
+                if (nd.prim < 0 || nd.prim >= f.n_prims) {
+                    *why = "node " + std::to_string(n) + ": primitive index out of bounds";
+                    return EUCL_ERR_INVALID_ARGUMENT;
+                }
+                int k = f.prims[nd.prim].kind;
+                leaf_hits += (k == EUCL_PRIM_SPHERE || k == EUCL_PRIM_CYLINDER) ? 2 : 1;
+                ++depth;
+            } else {
+                if (depth < 2 || nd.first < ent.node_first || nd.first >= n) {
+                    *why = "node " + std::to_string(n) + ": malformed post-order program";
+                    return EUCL_ERR_INVALID_ARGUMENT;
+                }
+                --depth;
+            }
+            max_depth = std::max(max_depth, depth);
+        }
+        if (depth != 1) {
+            *why = "entity " + std::to_string(e) + ": CSG program does not reduce to one shape";
+            return EUCL_ERR_INVALID_ARGUMENT;
+        }
+        // live lists (<= leaf_hits) + one merge output (<= leaf_hits + 2)
+        if (2 * leaf_hits + 2 > CSG_ARENA || max_depth > CSG_LIST_STACK || ent.node_root - ent.node_first + 1 > 64 * 4) {
+            *why = "entity " + std::to_string(e) + ": CSG program too large for the device evaluator (" +
+                   std::to_string(leaf_hits) + " leaf hits, nesting " + std::to_string(max_depth) + ")";
+            return EUCL_ERR_SCENE_LIMIT;
+        }
+    }
+    return EUCL_OK;
+}
+
+struct BlobWriter {
+    std::vector<uint8_t> bytes;
+    int reserve(size_t n) {
+        size_t off = align16(bytes.size());
+        bytes.resize(off + align16(n), 0);
+        return (int)off;
+    }
+    template <typename T>
+    int put(const T* src, size_t count) {
+        int off = reserve(sizeof(T) * std::max<size_t>(count, 1));
+        if (count) std::memcpy(bytes.data() + off, src, sizeof(T) * count);
+        return off;
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+int eucl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void eucl_scene_destroy(EuclScene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
+    for (auto a : s->arrays) cudaFreeArray(a);
+    if (s->d_blob) cudaFree(s->d_blob);
+    s->nodes.release();
+    s->small.release();
+    s->frame.release();
+    s->hit_ids.release();
+    if (s->h_small) cudaFreeHost(s->h_small);
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
+    if (!flat || !out) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: null argument");
+    *out = nullptr;
+    if (flat->dim != 3 && flat->dim != 4) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: dim must be 3 or 4");
+    const int n_dev = eucl_device_count();
+    if (n_dev <= 0) return fail(EUCL_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: device index out of range");
+    for (int t = 0; t < flat->n_textures; ++t)
+        if (flat->textures[t].width == 0 || flat->textures[t].height == 0 || !flat->texels)
+            return fail(EUCL_ERR_TEXTURE_MISSING, "texture slot " + std::to_string(t) + " was never filled");
+    std::string why;
+    int status = validate_programs(*flat, &why);
+    if (status != EUCL_OK) return fail(status, why);
+
+    EUCL_CUDA(cudaSetDevice(device));
+    EuclScene* s = new EuclScene();
+    s->device = device;
+    s->dim = flat->dim;
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+    auto bail = [&](int st, const std::string& msg) {
+        eucl_scene_destroy(s);
+        return fail(st, msg);
+    };
+#define EUCL_CUDA_S(expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return bail(_e == cudaErrorMemoryAllocation ? EUCL_ERR_OUT_OF_MEMORY : EUCL_ERR_CUDA,           \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                                \
+    } while (0)
+
+    EUCL_CUDA_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    EUCL_CUDA_S(cudaEventCreate(&s->ev[0]));
+    EUCL_CUDA_S(cudaEventCreate(&s->ev[1]));
+
+    // textures -> CUDA arrays + point-sampled texture objects
+    for (int t = 0; t < flat->n_textures; ++t) {
+        const EuclTexture& tx = flat->textures[t];
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        EUCL_CUDA_S(cudaMallocArray(&arr, &desc, tx.width, tx.height));
+        s->arrays.push_back(arr);
+        EUCL_CUDA_S(cudaMemcpy2DToArray(arr, 0, 0, flat->texels + tx.texel_offset, (size_t)tx.width * 4,
+                                        (size_t)tx.width * 4, tx.height, cudaMemcpyHostToDevice));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; // bilinear is done in f64 in the kernel
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t obj = 0;
+        EUCL_CUDA_S(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+        s->tex_objects.push_back(obj);
+    }
+
+    // pack the blob
+    BlobWriter w;
+    w.reserve(sizeof(SceneHeader));
+    SceneHeader h{};
+    h.dim = flat->dim;
+    h.n_prims = flat->n_prims;
+    h.n_nodes = flat->n_nodes;
+    h.n_entities = flat->n_entities;
+    h.n_materials = flat->n_materials;
+    h.n_transforms = flat->n_transforms;
+    h.n_expr_ops = flat->n_expr_ops;
+    h.n_surfaces = flat->n_surfaces;
+    h.n_color_ops = flat->n_color_ops;
+    h.n_mapped_textures = flat->n_mapped_textures;
+    h.n_textures = flat->n_textures;
+    h.background = flat->background;
+    const int np = std::max(flat->n_prims, 1);
+    std::vector<int32_t> kind((size_t)np, 0);
+    std::vector<double> v0((size_t)np * EUCL_MAX_DIM, 0.0), v1((size_t)np * EUCL_MAX_DIM, 0.0), s0((size_t)np, 0.0),
+        s1((size_t)np, 0.0);
+    for (int i = 0; i < flat->n_prims; ++i) {
+        const EuclPrim& p = flat->prims[i];
+        kind[(size_t)i] = p.kind;
+        for (int k = 0; k < EUCL_MAX_DIM; ++k) {
+            v0[(size_t)k * flat->n_prims + i] = p.v0[k];
+            v1[(size_t)k * flat->n_prims + i] = p.v1[k];
+        }
+        s0[(size_t)i] = p.s0;
+        s1[(size_t)i] = p.s1;
+    }
+    h.off_prim_kind = w.put(kind.data(), kind.size());
+    h.off_prim_v0 = w.put(v0.data(), v0.size());
+    h.off_prim_v1 = w.put(v1.data(), v1.size());
+    h.off_prim_s0 = w.put(s0.data(), s0.size());
+    h.off_prim_s1 = w.put(s1.data(), s1.size());
+    h.off_nodes = w.put(flat->nodes, (size_t)flat->n_nodes);
+    h.off_entities = w.put(flat->entities, (size_t)flat->n_entities);
+    h.off_materials = w.put(flat->materials, (size_t)flat->n_materials);
+    h.off_transforms = w.put(flat->transforms, (size_t)flat->n_transforms);
+    h.off_expr_ops = w.put(flat->expr_ops, (size_t)flat->n_expr_ops);
+    h.off_surfaces = w.put(flat->surfaces, (size_t)flat->n_surfaces);
+    h.off_color_ops = w.put(flat->color_ops, (size_t)flat->n_color_ops);
+    h.off_mapped = w.put(flat->mapped_textures, (size_t)flat->n_mapped_textures);
+    h.off_textures = w.put(flat->textures, (size_t)flat->n_textures);
+    h.off_tex_objects = w.put(s->tex_objects.data(), s->tex_objects.size());
+    h.off_perlin = w.put(flat->perlin_perm, 256);
+    int max_nodes = 1;
+    for (int e = 0; e < flat->n_entities; ++e)
+        max_nodes = std::max(max_nodes, flat->entities[e].node_root - flat->entities[e].node_first + 1);
+    h.max_entity_nodes = max_nodes;
+    h.blob_bytes = (int)w.bytes.size();
+    std::memcpy(w.bytes.data(), &h, sizeof h);
+    s->blob_bytes = h.blob_bytes;
+    s->smem_bytes = scene_smem_bytes(h.blob_bytes);
+    int smem_optin = 0;
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (s->smem_bytes > (size_t)smem_optin)
+        return bail(EUCL_ERR_SCENE_LIMIT, "scene tables (" + std::to_string(s->smem_bytes) +
+                                              " B) exceed the shared memory of one CTA (" + std::to_string(smem_optin) + " B)");
+    EUCL_CUDA_S(cudaMalloc((void**)&s->d_blob, w.bytes.size()));
+    EUCL_CUDA_S(cudaMemcpy(s->d_blob, w.bytes.data(), w.bytes.size(), cudaMemcpyHostToDevice));
+    EUCL_CUDA_S(configure_kernels(s->smem_bytes));
+    EUCL_CUDA_S(cudaMallocHost((void**)&s->h_small, sizeof(int32_t) * kSmallInts));
+#undef EUCL_CUDA_S
+    *out = s;
+    return EUCL_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+// Camera constants in the reference's order (d3/entity/camera.rs:61-67,174-182; d4: 167-173)
+void frame_params(const EuclCamera& cam, const EuclRenderOpts& o, FrameParams* fp) {
+    const int D = cam.dim;
+    std::memset(fp, 0, sizeof *fp);
+    const double w = (double)o.width, h = (double)o.height;
+    const double pi = 3.14159265358979323846264338327950288;
+    const double fov_rad = pi * (double)cam.fov_deg / 180.0;
+    volatile double diag = std::sqrt(w * w + h * h);
+    volatile double denom = 2.0 * std::tan(fov_rad / 2.0);
+    const double distance = diag / denom;
+    double right[EUCL_MAX_DIM] = {0, 0, 0, 0};
+    if (D == 3) {
+        volatile double cx = cam.forward[1] * cam.up[2] - cam.forward[2] * cam.up[1];
+        volatile double cy = cam.forward[2] * cam.up[0] - cam.forward[0] * cam.up[2];
+        volatile double cz = cam.forward[0] * cam.up[1] - cam.forward[1] * cam.up[0];
+        volatile double n2 = cx * cx + cy * cy;
+        n2 = n2 + cz * cz;
+        const double n = std::sqrt(n2);
+        right[0] = cx / n;
+        right[1] = cy / n;
+        right[2] = cz / n;
+    } else {
+        for (int k = 0; k < 4; ++k) right[k] = -cam.left[k];
+    }
+    for (int k = 0; k < D; ++k) {
+        fp->location[k] = cam.location[k];
+        volatile double step = cam.forward[k] * distance;
+        fp->center[k] = cam.location[k] + step;
+        fp->up[k] = cam.up[k];
+        fp->right[k] = right[k];
+    }
+    // Duration * 1000 -> whole seconds -> / 1000 (d3/entity/surface.rs:32)
+    fp->time_millis = std::floor(o.time_seconds * 1000.0) / 1000.0;
+    fp->width = (int)o.width;
+    fp->height = (int)o.height;
+    fp->max_depth = (int)cam.max_depth;
+}
+
+size_t arena_bytes(int dim, size_t cap) {
+    size_t per = (size_t)dim * 16 * 2 + 4 + 8 + sizeof(NodeMeta) + 32;
+    return per * cap + 16 * 16;
+}
+
+Workspace carve(EuclScene* s, int dim, int cap) {
+    Workspace ws{};
+    ws.capacity = cap;
+    uint8_t* p = (uint8_t*)s->nodes.ptr;
+    auto take = [&](size_t bytes) {
+        uint8_t* r = p;
+        p += align16(bytes);
+        return r;
+    };
+    ws.ray_od = (double2*)take((size_t)dim * 16 * cap);
+    ws.hit_pn = (double2*)take((size_t)dim * 16 * cap);
+    ws.res_rg = (double2*)take((size_t)16 * cap);
+    ws.res_ba = (double2*)take((size_t)16 * cap);
+    ws.meta = (NodeMeta*)take(sizeof(NodeMeta) * (size_t)cap);
+    ws.hit_ei = (int2*)take((size_t)8 * cap);
+    ws.ray_cur = (int32_t*)take((size_t)4 * cap);
+    int32_t* small = (int32_t*)s->small.ptr;
+    ws.count = small + SmallLayout::count;
+    ws.level_off = small + SmallLayout::level_off;
+    ws.overflow = small + SmallLayout::overflow;
+    ws.cam_entity = small + SmallLayout::cam_entity;
+    ws.undefined_count = (unsigned long long*)(small + SmallLayout::undefined64);
+    ws.mega_level_counts = (unsigned long long*)(small + SmallLayout::mega64);
+    return ws;
+}
+
+int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* d_rgb, int32_t* d_hit,
+                EuclStats* stats, bool sync_and_time) {
+    (void)sync_and_time;
+    const int dim = s->dim;
+    FrameParams fp;
+    frame_params(*cam, *o, &fp);
+    const int width = (int)o->width;
+    const uint32_t my_rows = eucl_band_rows_for_rank(o);
+    EuclStats st{};
+    st.levels = cam->max_depth + 1;
+    EUCL_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    if (my_rows > 0) {
+        // chunking: whole local rows, about EUCL_CHUNK_PIXELS primaries per chunk
+        const long long chunk_pixels_target = std::max(1, env_int("EUCL_CHUNK_PIXELS", 1 << 21));
+        int rows_per_chunk = (int)std::max<long long>(1, chunk_pixels_target / width);
+        rows_per_chunk = std::min<int>(rows_per_chunk, (int)my_rows);
+        const long long chunk_pixels = (long long)rows_per_chunk * width;
+        if (chunk_pixels > (1ll << 30)) return fail(EUCL_ERR_INVALID_ARGUMENT, "frame rows too wide");
+        EUCL_CUDA(s->small.ensure(sizeof(int32_t) * kSmallInts));
+        if (s->arena_factor <= 0.0) s->arena_factor = std::max(1.0, (double)env_int("EUCL_ARENA_FACTOR_X10", 45) / 10.0);
+        Launch l{s->stream, s->d_blob, s->smem_bytes, s->sm_count * env_int("EUCL_BLOCKS_PER_SM", 8)};
+
+        for (int row0 = 0; row0 < (int)my_rows; row0 += rows_per_chunk) {
+            ChunkParams cp{};
+            cp.local_row0 = row0;
+            cp.n_rows = std::min<int>(rows_per_chunk, (int)my_rows - row0);
+            cp.band_rows = o->band_rows ? (int)o->band_rows : (int)o->height;
+            cp.band_rank = (int)o->band_rank;
+            cp.band_world = o->band_world ? (int)o->band_world : 1;
+            cp.compact_rows = o->compact_rows;
+            cp.n_pixels = cp.n_rows * width;
+            for (;;) { // retry with a larger arena when a level overflowed
+                long long want = (long long)std::ceil((double)chunk_pixels * s->arena_factor) + 1024;
+                if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) want = 16;
+                if (want > 0x7fff0000ll) return fail(EUCL_ERR_OUT_OF_MEMORY, "node arena would exceed 2^31 nodes; lower EUCL_CHUNK_PIXELS");
+                if ((int)want > s->arena_capacity) {
+                    EUCL_CUDA(cudaStreamSynchronize(s->stream));
+                    EUCL_CUDA(s->nodes.ensure(arena_bytes(dim, (size_t)want)));
+                    s->arena_capacity = (int)want;
+                }
+                Workspace ws = carve(s, dim, s->arena_capacity);
+                EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));
+                launch_camera_entity(dim, l, fp, ws);
+                st.launches += 1;
+                if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) {
+                    if (cam->max_depth > 24) return fail(EUCL_ERR_SCENE_LIMIT, "megakernel pipeline supports max_depth <= 24");
+                    launch_megakernel(dim, l, fp, cp, ws, d_rgb, d_hit);
+                    st.launches += 1;
+                } else {
+                    launch_raygen(dim, l, fp, cp, ws, d_hit);
+                    for (int level = 0; level < (int)cam->max_depth; ++level) {
+                        launch_intersect(dim, l, ws, level);
+                        launch_shade(dim, l, fp, cp, ws, level, d_hit);
+                    }
+                    launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
+                    for (int level = (int)cam->max_depth - 1; level >= 1; --level) launch_resolve(dim, l, ws, level);
+                    launch_final(dim, l, fp, cp, ws, d_rgb);
+                    st.launches += 3 + 2 * cam->max_depth + (cam->max_depth > 0 ? cam->max_depth - 1 : 0);
+                }
+                EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
+                                          s->stream));
+                EUCL_CUDA(cudaStreamSynchronize(s->stream));
+                EUCL_CUDA(cudaGetLastError());
+                if (s->h_small[SmallLayout::overflow]) {
+                    // levels after the overflowing one were skipped, so the counts are a lower bound only
+                    long long need = 0;
+                    for (uint32_t lv = 0; lv <= cam->max_depth; ++lv) need += s->h_small[SmallLayout::count + lv];
+                    double factor = (double)need / (double)cp.n_pixels * 1.05 + 0.05;
+                    s->arena_factor = std::max(s->arena_factor * 1.5, factor);
+                    st.retries += 1;
+                    if (st.retries > 32) return fail(EUCL_ERR_OUT_OF_MEMORY, "node arena keeps overflowing");
+                    continue;
+                }
+                break;
+            }
+            st.pixels += (uint64_t)cp.n_pixels;
+            for (uint32_t lv = 0; lv <= cam->max_depth; ++lv) {
+                uint64_t c = o->pipeline == EUCL_PIPELINE_MEGAKERNEL
+                                 ? ((const unsigned long long*)(s->h_small + SmallLayout::mega64))[lv]
+                                 : (uint64_t)s->h_small[SmallLayout::count + lv];
+                st.level_counts[lv] += c;
+                st.nodes += c;
+                if (lv < cam->max_depth) st.segments += c;
+            }
+        }
+    }
+    EUCL_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    EUCL_CUDA(cudaEventSynchronize(s->ev[1]));
+    EUCL_CUDA(cudaEventElapsedTime(&st.ms_total, s->ev[0], s->ev[1]));
+    if (stats) *stats = st;
+    return EUCL_OK;
+}
+
+int check_args(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o) {
+    if (!s || !cam || !o) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: null argument");
+    if (cam->dim != s->dim) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: camera dimension does not match the scene");
+    if (o->width == 0 || o->height == 0 || o->width > (1u << 20) || o->height > (1u << 20))
+        return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: bad frame size");
+    if (cam->max_depth + 1 > EUCL_MAX_LEVELS) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: max_depth too large");
+    if (o->band_world > 1 && o->band_rank >= o->band_world) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: band_rank >= band_world");
+    if (o->pipeline != EUCL_PIPELINE_WAVEFRONT && o->pipeline != EUCL_PIPELINE_MEGAKERNEL)
+        return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: unknown pipeline");
+    return EUCL_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int eucl_render_device(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, void* d_out_rgb8, void* d_out_hit_ids,
+                       EuclStats* stats) {
+    int st = check_args(s, cam, o);
+    if (st != EUCL_OK) return st;
+    if (!d_out_rgb8) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render_device: null output");
+    EUCL_CUDA(cudaSetDevice(s->device));
+    return render_impl(s, cam, o, (uint8_t*)d_out_rgb8, o->want_hit_ids ? (int32_t*)d_out_hit_ids : nullptr, stats, true);
+}
+
+int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* out_rgb8, int32_t* out_hit_ids,
+                EuclStats* stats) {
+    int st = check_args(s, cam, o);
+    if (st != EUCL_OK) return st;
+    if (!out_rgb8) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: null output");
+    EUCL_CUDA(cudaSetDevice(s->device));
+    const size_t rows = o->compact_rows ? eucl_band_rows_for_rank(o) : o->height;
+    const size_t pixels = rows * (size_t)o->width;
+    const bool want_hit = o->want_hit_ids && out_hit_ids;
+    EUCL_CUDA(s->frame.ensure(pixels * 3));
+    if (want_hit) EUCL_CUDA(s->hit_ids.ensure(pixels * 4));
+    const bool partial = !o->compact_rows && o->band_world > 1;
+    if (partial) { // rows of other ranks are left untouched in the caller's buffer: stage them in
+        EUCL_CUDA(cudaMemcpyAsync(s->frame.ptr, out_rgb8, pixels * 3, cudaMemcpyHostToDevice, s->stream));
+        if (want_hit) EUCL_CUDA(cudaMemcpyAsync(s->hit_ids.ptr, out_hit_ids, pixels * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    EuclRenderOpts opts = *o;
+    opts.want_hit_ids = want_hit ? 1 : 0;
+    st = render_impl(s, cam, &opts, (uint8_t*)s->frame.ptr, want_hit ? (int32_t*)s->hit_ids.ptr : nullptr, stats, true);
+    if (st != EUCL_OK) return st;
+    EUCL_CUDA(cudaMemcpyAsync(out_rgb8, s->frame.ptr, pixels * 3, cudaMemcpyDeviceToHost, s->stream));
+    if (want_hit) EUCL_CUDA(cudaMemcpyAsync(out_hit_ids, s->hit_ids.ptr, pixels * 4, cudaMemcpyDeviceToHost, s->stream));
+    EUCL_CUDA(cudaStreamSynchronize(s->stream));
+    return EUCL_OK;
+}
+
+int eucl_ipc_export(void* d_ptr, uint8_t handle[EUCL_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= EUCL_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d_ptr || !handle) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    EUCL_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memset(handle, 0, EUCL_IPC_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof h);
+    return EUCL_OK;
+}
+
+int eucl_ipc_open(const uint8_t handle[EUCL_IPC_HANDLE_BYTES], int device, void** d_ptr) {
+    if (!handle || !d_ptr) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_ipc_open: null argument");
+    EUCL_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    EUCL_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return EUCL_OK;
+}
+
+int eucl_ipc_close(void* d_ptr) {
+    if (!d_ptr) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_ipc_close: null argument");
+    EUCL_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return EUCL_OK;
+}
+
+int eucl_fp64_peak(int device, double* dadd_tops, double* dmul_tops, double* dfma_tops) {
+    if (!dadd_tops || !dmul_tops || !dfma_tops) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_fp64_peak: null argument");
+    if (eucl_device_count() <= 0) return fail(EUCL_ERR_NO_DEVICE, "no CUDA device available");
+    EUCL_CUDA(cudaSetDevice(device));
+    if (fp64_peak(dadd_tops, dmul_tops, dfma_tops) != 0) return fail(EUCL_ERR_CUDA, "fp64 microbenchmark failed");
+    return EUCL_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,643 @@
+// CUDA kernels of the trace loop for sm_100a.
+//
+// Wavefront pipeline (default): ray generation -> per level { intersect, shade + emit } ->
+// bottom-up resolve of the ray tree -> composite + RGB8 pack.  A one-thread-per-pixel megakernel
+// over the same device functions exists as a cross-check (EUCL_PIPELINE_MEGAKERNEL).
+//
+// Reference semantics: Environment::render / trace_screen_point / Universe::trace*
+// (src/universe/mod.rs:85-184,229-271,300-397) and ComposableSurface::get_color
+// (src/universe/entity/surface.rs:62-162).  Compiled with -fmad=false.
+#include "pipeline.cuh"
+#include "shade.cuh"
+
+namespace eucl {
+
+namespace {
+
+extern __shared__ __align__(16) unsigned char g_smem[];
+
+// ---------------------------------------------------------------------------------------------
+// node arena access (planes of double2 -> 128-bit coalesced transactions)
+
+template <int D>
+__device__ __forceinline__ void store_ray(const Workspace& ws, int node, const Vec<D>& o, const Vec<D>& d, int cur) {
+    double v[2 * D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        v[k] = o[k];
+        v[D + k] = d[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) ws.ray_od[(size_t)k * ws.capacity + node] = make_double2(v[2 * k], v[2 * k + 1]);
+    ws.ray_cur[node] = cur;
+}
+template <int D>
+__device__ __forceinline__ void load_ray(const Workspace& ws, int node, Vec<D>& o, Vec<D>& d) {
+    double v[2 * D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double2 t = ws.ray_od[(size_t)k * ws.capacity + node];
+        v[2 * k] = t.x;
+        v[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        o[k] = v[k];
+        d[k] = v[D + k];
+    }
+}
+template <int D>
+__device__ __forceinline__ void store_hit(const Workspace& ws, int node, const Vec<D>& p, const Vec<D>& n) {
+    double v[2 * D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        v[k] = p[k];
+        v[D + k] = n[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) ws.hit_pn[(size_t)k * ws.capacity + node] = make_double2(v[2 * k], v[2 * k + 1]);
+}
+template <int D>
+__device__ __forceinline__ void load_hit(const Workspace& ws, int node, Vec<D>& p, Vec<D>& n) {
+    double v[2 * D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double2 t = ws.hit_pn[(size_t)k * ws.capacity + node];
+        v[2 * k] = t.x;
+        v[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        p[k] = v[k];
+        n[k] = v[D + k];
+    }
+}
+__device__ __forceinline__ void store_res(const Workspace& ws, int node, const Rgba& c) {
+    ws.res_rg[node] = make_double2(c.r, c.g);
+    ws.res_ba[node] = make_double2(c.b, c.a);
+}
+__device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
+    double2 rg = ws.res_rg[node], ba = ws.res_ba[node];
+    return Rgba{rg.x, rg.y, ba.x, ba.y};
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared device logic (used by the wavefront kernels and the megakernel)
+
+// trace_closest: closest first-hit over all surfaced entities, then the geometry of the winner
+// and its orientation relative to the ray (mod.rs:114-125).
+template <int D>
+__device__ __forceinline__ int intersect_ray(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, bool& exiting, Vec<D>& p,
+                                             Vec<D>& n_raw) {
+    const ClosestHit h = closest_hit<D>(sv, o, d);
+    if (h.entity < 0) return -1;
+    hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n_raw);
+    exiting = angle_between(d, n_raw) < kFracPi2;
+    return h.entity;
+}
+
+template <int D>
+struct ChildRay {
+    Vec<D> o, d;
+    int cur;
+};
+template <int D>
+struct ShadeOut {
+    double ratio;
+    unsigned q;
+    unsigned flags;
+    Rgba sc; // valid when flags & NODE_HAS_SC
+    bool t_emit, r_emit;
+    ChildRay<D> t, r;
+};
+
+// ComposableSurface::get_color up to (not including) the recursive trace calls
+// (surface.rs:62-162): decides which children exist and where they start.
+template <int D>
+__device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
+                                          bool exiting, const Vec<D>& p, const Vec<D>& n_raw, ShadeOut<D>& out) {
+    const EuclSurface& sf = sv.surfaces[sv.entities[ent].surface];
+    const Vec<D> n_closer = exiting ? -n_raw : n_raw;
+    // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
+    const double ratio = fmax(fmin(reflection_ratio<D>(sf, dir, n_closer, exiting), 1.0), 0.0);
+    out.ratio = ratio;
+    out.q = 0u;
+    out.flags = 0u;
+    out.t_emit = false;
+    out.r_emit = false;
+    bool have_t = false;
+    if (!(ratio >= 1.0)) { // get_intersection_color
+        const Rgba sc = surface_color<D>(sv, sf, dir, p, n_raw, n_closer, time_millis);
+        const unsigned q = to_pixel4(sc);
+        out.q = q;
+        if ((q >> 24) == 255u) {
+            out.sc = sc;
+            out.flags |= NODE_HAS_SC;
+            have_t = true;
+        } else {
+            Vec<D> td = threshold_direction<D>(sf, dir, n_closer, exiting);
+            const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
+            const int dest = exiting ? material_at<D>(sv, new_origin) : ent;
+            if (dest >= 0) {
+                material_exit<D>(sv, cur, td);
+                material_enter<D>(sv, dest, td);
+                out.t_emit = true;
+                out.t.o = new_origin;
+                out.t.d = td;
+                out.t.cur = dest;
+                have_t = true;
+            }
+        }
+    }
+    if (!(ratio <= 0.0)) { // get_reflection_color
+        out.r_emit = true;
+        out.r.o = p + n_closer * kApproxEpsilon * 128.0;
+        out.r.d = reflection_direction<D>(dir, n_closer);
+        out.r.cur = cur;
+    }
+    if (!have_t && !out.r_emit) out.flags |= NODE_UNDEFINED | NODE_LEAF;
+}
+
+// Colour of an inner node from its children (surface.rs:104-114,150-161)
+__device__ __forceinline__ Rgba transmit_over(unsigned q, const Rgba& child) {
+    return from_premultiplied(over_pre(into_premultiplied(new_u8(q)), into_premultiplied(new_u8(to_pixel4(child)))));
+}
+
+// trace_unknown tail (mod.rs:260-270) + to_pixel (mod.rs:342): composite over opaque white
+__device__ __forceinline__ void final_rgb8(const Rgba& fg, bool composite, uint8_t* out) {
+    Rgba c = fg;
+    if (composite) c = from_premultiplied(over_pre(into_premultiplied(fg), Pre{1.0, 1.0, 1.0, 1.0}));
+    out[0] = (uint8_t)channel_to_u8(c.r);
+    out[1] = (uint8_t)channel_to_u8(c.g);
+    out[2] = (uint8_t)channel_to_u8(c.b);
+}
+
+// Camera::get_ray_vector (d3/entity/camera.rs:164-185, d4/entity/camera.rs:155-176)
+template <int D>
+__device__ __forceinline__ Vec<D> camera_ray(const FrameParams& fp, int x, int y) {
+    const double rel_x = (double)(x - fp.width / 2) + (double)(1 - fp.width % 2) / 2.0;
+    const double rel_y = (double)(y - fp.height / 2) + (double)(1 - fp.height % 2) / 2.0;
+    Vec<D> loc, center, up, right;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        loc[k] = fp.location[k];
+        center[k] = fp.center[k];
+        up[k] = fp.up[k];
+        right[k] = fp.right[k];
+    }
+    const Vec<D> screen_point = center + (up * rel_y) + (right * rel_x);
+    return normalize(screen_point - loc);
+}
+
+__device__ __forceinline__ Rgba checkerboard(int x, int y) { // mod.rs:387-395
+    if ((x / 8 + y / 8) % 2 == 0) return Rgba{0.0, 0.0, 0.0, 1.0};
+    return Rgba{1.0, 0.0, 1.0, 1.0};
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+
+// material_at(camera location) is the same for every pixel of a frame: computed once.
+template <int D>
+__global__ void __launch_bounds__(32) k_camera_entity(const uint8_t* __restrict__ blob, FrameParams fp, Workspace ws) {
+    const SceneView& sv = stage_scene(blob, g_smem);
+    if (threadIdx.x == 0) {
+        Vec<D> loc;
+#pragma unroll
+        for (int k = 0; k < D; ++k) loc[k] = fp.location[k];
+        *ws.cam_entity = material_at<D>(sv, loc);
+    }
+}
+
+// K1: one primary ray per pixel of the chunk; level 0 of the node arena is the pixel order.
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
+                                                   Workspace ws, int32_t* __restrict__ hit_ids_out) {
+    const SceneView& sv = stage_scene(blob, g_smem);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ws.count[0] = cp.n_pixels;
+        ws.level_off[0] = 0;
+    }
+    const int belongs_to = *ws.cam_entity;
+    Vec<D> loc;
+#pragma unroll
+    for (int k = 0; k < D; ++k) loc[k] = fp.location[k];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
+        const int local_row = cp.local_row0 + i / fp.width;
+        const int x = i % fp.width;
+        const int y = frame_row_of_local(cp, local_row);
+        if (belongs_to < 0) {
+            store_res(ws, i, checkerboard(x, y));
+            ws.meta[i] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF | NODE_FINAL_RGB};
+            ws.ray_cur[i] = -1;
+            if (hit_ids_out) hit_ids_out[(size_t)(cp.compact_rows ? local_row : y) * fp.width + x] = -2;
+            continue;
+        }
+        Vec<D> dir = camera_ray<D>(fp, x, y);
+        material_enter<D>(sv, belongs_to, dir);
+        store_ray<D>(ws, i, loc, dir, belongs_to);
+    }
+}
+
+// K2: closest hit of every ray of one level.
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level) {
+    if (*ws.overflow) return; // an earlier level did not fit: the host grows the arena and retries
+    const int off = ws.level_off[level], cnt = ws.count[level];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.level_off[level + 1] = off + cnt;
+    if (blockIdx.x * blockDim.x >= cnt) return;
+    const SceneView& sv = stage_scene(blob, g_smem);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const int node = off + i;
+        if (ws.ray_cur[node] < 0) continue;
+        Vec<D> o, d, p, n;
+        load_ray<D>(ws, node, o, d);
+        bool exiting = false;
+        const int ent = intersect_ray<D>(sv, o, d, exiting, p, n);
+        ws.hit_ei[node] = make_int2(ent, exiting ? 1 : 0);
+        if (ent >= 0) store_hit<D>(ws, node, p, n);
+    }
+}
+
+// K3: shade every node of one level and append its children to the next level.  Children are
+// appended with one atomicAdd per warp (ballot + popc ranks).
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
+                                                  Workspace ws, int level, int32_t* __restrict__ hit_ids_out) {
+    const int off = ws.level_off[level], cnt = ws.count[level];
+    if (blockIdx.x * blockDim.x >= cnt) return;
+    if (level > 0 && *ws.overflow) return; // set by an EARLIER kernel (level 0 always fits); see k_intersect
+    const SceneView& sv = stage_scene(blob, g_smem);
+    const bool last_level = level >= fp.max_depth; // depth 0: background without intersecting (mod.rs:157,183)
+    const int next_off = last_level ? 0 : ws.level_off[level + 1];
+    const unsigned lane = threadIdx.x & 31u;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cnt; base += stride) {
+        const int i = base + (int)lane;
+        const int node = off + i;
+        const bool valid = i < cnt && ws.ray_cur[node] >= 0;
+        ShadeOut<D> so;
+        so.t_emit = false;
+        so.r_emit = false;
+        bool shaded = false;
+        if (valid) {
+            Vec<D> o, d;
+            load_ray<D>(ws, node, o, d);
+            const int cur = ws.ray_cur[node];
+            const int2 ei = last_level ? make_int2(-1, 0) : ws.hit_ei[node];
+            if (level == 0 && hit_ids_out) {
+                const int local_row = cp.local_row0 + i / fp.width;
+                const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
+                hit_ids_out[(size_t)orow * fp.width + i % fp.width] = ei.x;
+            }
+            if (ei.x < 0) {
+                store_res(ws, node, mapped_color<D>(sv, sv.background, d)); // background.get_color(direction.to_point())
+                ws.meta[node] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF};
+            } else {
+                Vec<D> p, n;
+                load_hit<D>(ws, node, p, n);
+                shade_hit<D>(sv, fp.time_millis, d, cur, ei.x, ei.y != 0, p, n, so);
+                shaded = true;
+            }
+        }
+        // warp-aggregated append of the children to level + 1: one atomicAdd per warp
+        const unsigned tmask = __ballot_sync(0xffffffffu, so.t_emit), rmask = __ballot_sync(0xffffffffu, so.r_emit);
+        const int nt = __popc(tmask), total = nt + __popc(rmask);
+        int slot = 0;
+        if (total > 0) {
+            if (lane == 0) slot = atomicAdd(&ws.count[level + 1], total);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+        }
+        const bool fits = total > 0 && (long long)next_off + slot + total <= (long long)ws.capacity;
+        if (total > 0 && !fits && lane == 0) *ws.overflow = 1;
+        if (shaded) {
+            const unsigned lt = (1u << lane) - 1u;
+            int tchild = -1, rchild = -1;
+            if (fits && so.t_emit) {
+                tchild = next_off + slot + __popc(tmask & lt);
+                store_ray<D>(ws, tchild, so.t.o, so.t.d, so.t.cur);
+            }
+            if (fits && so.r_emit) {
+                rchild = next_off + slot + nt + __popc(rmask & lt);
+                store_ray<D>(ws, rchild, so.r.o, so.r.d, so.r.cur);
+            }
+            unsigned flags = so.flags;
+            if (flags & NODE_HAS_SC) {
+                store_res(ws, node, so.sc);
+                if (!so.r_emit) flags |= NODE_LEAF; // opaque without a mirror term: the colour is final
+            }
+            if (flags & NODE_UNDEFINED) {
+                store_res(ws, node, Rgba{0.0, 0.0, 0.0, 0.0});
+                atomicAdd(ws.undefined_count, 1ull);
+            }
+            ws.meta[node] = NodeMeta{so.ratio, tchild, rchild, so.q, flags};
+        }
+    }
+}
+
+// K4: colour of the inner nodes of one level from the (already final) colours of level + 1.
+__global__ void __launch_bounds__(256) k_resolve(Workspace ws, int level) {
+    if (*ws.overflow) return;
+    const int off = ws.level_off[level], cnt = ws.count[level];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const int node = off + i;
+        const NodeMeta m = ws.meta[node];
+        if (m.flags & NODE_LEAF) continue;
+        bool have_t = false;
+        Rgba t{0.0, 0.0, 0.0, 0.0};
+        if (m.flags & NODE_HAS_SC) {
+            t = load_res(ws, node);
+            have_t = true;
+        } else if (m.tchild >= 0) {
+            t = transmit_over(m.q, load_res(ws, m.tchild));
+            have_t = true;
+        }
+        Rgba out = t;
+        if (m.rchild >= 0) {
+            const Rgba r = load_res(ws, m.rchild);
+            out = have_t ? combine_palette_color(r, t, m.ratio) : r;
+        }
+        store_res(ws, node, out);
+    }
+}
+
+// K5: resolve level 0, composite over white, quantise and pack RGB8 rows (row 0 = bottom).
+__global__ void __launch_bounds__(256) k_final(FrameParams fp, ChunkParams cp, Workspace ws, uint8_t* __restrict__ out_rgb8) {
+    if (*ws.overflow) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
+        const NodeMeta m = ws.meta[i];
+        Rgba c;
+        if (m.flags & NODE_LEAF) {
+            c = load_res(ws, i);
+        } else {
+            bool have_t = false;
+            Rgba t{0.0, 0.0, 0.0, 0.0};
+            if (m.flags & NODE_HAS_SC) {
+                t = load_res(ws, i);
+                have_t = true;
+            } else if (m.tchild >= 0) {
+                t = transmit_over(m.q, load_res(ws, m.tchild));
+                have_t = true;
+            }
+            c = t;
+            if (m.rchild >= 0) {
+                const Rgba r = load_res(ws, m.rchild);
+                c = have_t ? combine_palette_color(r, t, m.ratio) : r;
+            }
+        }
+        const int local_row = cp.local_row0 + i / fp.width;
+        const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
+        final_rgb8(c, !(m.flags & NODE_FINAL_RGB), out_rgb8 + ((size_t)orow * fp.width + i % fp.width) * 3);
+    }
+}
+
+// Cross-check pipeline: one thread walks the whole ray tree of its pixel depth-first with an
+// explicit stack (transmitted subtree first, then the reflected one, as the reference recurses).
+constexpr int kMegaMaxDepth = 24;
+template <int D>
+struct MegaFrame {
+    double ratio;
+    unsigned q;
+    unsigned state; // bit 0: waiting for the reflected child (else the transmitted one); bit 1: have T; bit 2: reflect pending
+    Rgba t;
+    ChildRay<D> r;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
+                                                       Workspace ws, uint8_t* __restrict__ out_rgb8,
+                                                       int32_t* __restrict__ hit_ids_out) {
+    const SceneView& sv = stage_scene(blob, g_smem);
+    const int belongs_to = *ws.cam_entity;
+    unsigned long long local_counts[kMegaMaxDepth + 1];
+    for (int l = 0; l <= kMegaMaxDepth; ++l) local_counts[l] = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
+        const int local_row = cp.local_row0 + i / fp.width;
+        const int x = i % fp.width;
+        const int y = frame_row_of_local(cp, local_row);
+        const size_t opix = (size_t)(cp.compact_rows ? local_row : y) * fp.width + x;
+        if (belongs_to < 0) {
+            final_rgb8(checkerboard(x, y), false, out_rgb8 + opix * 3);
+            if (hit_ids_out) hit_ids_out[opix] = -2;
+            local_counts[0]++;
+            continue;
+        }
+        MegaFrame<D> stack[kMegaMaxDepth];
+        Vec<D> o, d;
+#pragma unroll
+        for (int k = 0; k < D; ++k) o[k] = fp.location[k];
+        d = camera_ray<D>(fp, x, y);
+        material_enter<D>(sv, belongs_to, d);
+        int cur = belongs_to, level = 0;
+        Rgba val{0.0, 0.0, 0.0, 0.0};
+        for (;;) {
+            // ---- descend: evaluate the node for ray (o, d, cur) at `level`
+            bool leaf = true;
+            local_counts[level]++;
+            int ent = -1;
+            bool exiting = false;
+            Vec<D> p, n;
+            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n);
+            if (level == 0 && hit_ids_out) hit_ids_out[opix] = ent;
+            if (ent < 0) {
+                val = mapped_color<D>(sv, sv.background, d);
+            } else {
+                ShadeOut<D> so;
+                shade_hit<D>(sv, fp.time_millis, d, cur, ent, exiting, p, n, so);
+                if (so.flags & NODE_UNDEFINED) {
+                    val = Rgba{0.0, 0.0, 0.0, 0.0};
+                    atomicAdd(ws.undefined_count, 1ull);
+                } else if (!so.t_emit && !so.r_emit) {
+                    val = so.sc; // opaque, no mirror
+                } else {
+                    MegaFrame<D>& f = stack[level];
+                    f.ratio = so.ratio;
+                    f.q = so.q;
+                    f.state = 0u;
+                    if (so.flags & NODE_HAS_SC) {
+                        f.t = so.sc;
+                        f.state |= 2u;
+                    }
+                    if (so.r_emit) {
+                        f.r = so.r;
+                        f.state |= 4u;
+                    }
+                    if (so.t_emit) {
+                        o = so.t.o;
+                        d = so.t.d;
+                        cur = so.t.cur;
+                    } else {
+                        f.state |= 1u;
+                        o = so.r.o;
+                        d = so.r.d;
+                        cur = so.r.cur;
+                    }
+                    ++level;
+                    leaf = false;
+                }
+            }
+            if (!leaf) continue;
+            // ---- ascend with `val` until a pending reflected child is found
+            bool done = false;
+            for (;;) {
+                if (level == 0) {
+                    done = true;
+                    break;
+                }
+                --level;
+                MegaFrame<D>& f = stack[level];
+                if (!(f.state & 1u)) { // the transmitted child returned
+                    f.t = transmit_over(f.q, val);
+                    f.state |= 2u;
+                    if (f.state & 4u) {
+                        f.state |= 1u;
+                        o = f.r.o;
+                        d = f.r.d;
+                        cur = f.r.cur;
+                        ++level;
+                        break;
+                    }
+                    val = f.t;
+                } else { // the reflected child returned
+                    val = (f.state & 2u) ? combine_palette_color(val, f.t, f.ratio) : val;
+                }
+            }
+            if (done) break;
+        }
+        final_rgb8(val, true, out_rgb8 + opix * 3);
+    }
+    for (int l = 0; l <= fp.max_depth && l <= kMegaMaxDepth; ++l) {
+        // per-level node counts, warp-reduced
+        unsigned long long v = local_counts[l];
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_down_sync(0xffffffffu, v, s);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ws.mega_level_counts + l, v);
+    }
+}
+
+// FP64 issue-rate microbenchmark: 8 independent dependency chains per thread
+template <int OP>
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0,
+           a7 = a0 + 7.0;
+    const double m = 1.0000000001, c = 1.0e-9;
+    for (int i = 0; i < iters; ++i) {
+        if (OP == 0) {
+            a0 = __dadd_rn(a0, c); a1 = __dadd_rn(a1, c); a2 = __dadd_rn(a2, c); a3 = __dadd_rn(a3, c);
+            a4 = __dadd_rn(a4, c); a5 = __dadd_rn(a5, c); a6 = __dadd_rn(a6, c); a7 = __dadd_rn(a7, c);
+        } else if (OP == 1) {
+            a0 = __dmul_rn(a0, m); a1 = __dmul_rn(a1, m); a2 = __dmul_rn(a2, m); a3 = __dmul_rn(a3, m);
+            a4 = __dmul_rn(a4, m); a5 = __dmul_rn(a5, m); a6 = __dmul_rn(a6, m); a7 = __dmul_rn(a7, m);
+        } else {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+inline int grid_for(int n, int block, int grid_max) {
+    long long g = ((long long)n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > grid_max) g = grid_max;
+    return (int)g;
+}
+
+} // namespace
+
+#define EUCL_DISPATCH_DIM(dim, CALL3, CALL4) \
+    do {                                     \
+        if ((dim) == 3) { CALL3; }           \
+        else { CALL4; }                      \
+    } while (0)
+
+void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws) {
+    EUCL_DISPATCH_DIM(dim, (k_camera_entity<3><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, fp, ws)),
+                      (k_camera_entity<4><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, fp, ws)));
+}
+void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                   int32_t* hit_ids_out) {
+    const int grid = grid_for(cp.n_pixels, kBlock, l.grid_max);
+    EUCL_DISPATCH_DIM(dim, (k_raygen<3><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)),
+                      (k_raygen<4><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)));
+}
+void launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
+    EUCL_DISPATCH_DIM(dim, (k_intersect<3><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level)),
+                      (k_intersect<4><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level)));
+}
+void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
+                  int32_t* hit_ids_out) {
+    EUCL_DISPATCH_DIM(dim,
+                      (k_shade<3><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
+                      (k_shade<4><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
+}
+void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level) {
+    (void)dim;
+    k_resolve<<<l.grid_max, 256, 0, l.stream>>>(ws, level);
+}
+void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                  uint8_t* out_rgb8) {
+    (void)dim;
+    k_final<<<grid_for(cp.n_pixels, 256, l.grid_max), 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
+}
+void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                       uint8_t* out_rgb8, int32_t* hit_ids_out) {
+    const int grid = grid_for(cp.n_pixels, kBlock, 1 << 30);
+    EUCL_DISPATCH_DIM(
+        dim, (k_megakernel<3><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, out_rgb8, hit_ids_out)),
+        (k_megakernel<4><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, out_rgb8, hit_ids_out)));
+}
+
+cudaError_t configure_kernels(size_t smem_bytes) {
+    if (smem_bytes <= 48 * 1024) return cudaSuccess;
+    const int v = (int)smem_bytes;
+    cudaError_t e;
+#define EUCL_SET_SMEM(K) \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, v)) != cudaSuccess) return e
+    EUCL_SET_SMEM(k_camera_entity<3>);
+    EUCL_SET_SMEM(k_camera_entity<4>);
+    EUCL_SET_SMEM(k_raygen<3>);
+    EUCL_SET_SMEM(k_raygen<4>);
+    EUCL_SET_SMEM(k_intersect<3>);
+    EUCL_SET_SMEM(k_intersect<4>);
+    EUCL_SET_SMEM(k_shade<3>);
+    EUCL_SET_SMEM(k_shade<4>);
+    EUCL_SET_SMEM(k_megakernel<3>);
+    EUCL_SET_SMEM(k_megakernel<4>);
+#undef EUCL_SET_SMEM
+    return cudaSuccess;
+}
+
+int fp64_peak(double* dadd, double* dmul, double* dfma) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    double* buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double* outs[3] = {dadd, dmul, dfma};
+    for (int op = 0; op < 3; ++op) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            if (op == 0) k_fp64_peak<0><<<blocks, threads>>>(buf, iters, 1.0);
+            else if (op == 1) k_fp64_peak<1><<<blocks, threads>>>(buf, iters, 1.0);
+            else k_fp64_peak<2><<<blocks, threads>>>(buf, iters, 1.0);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double ops = (double)blocks * threads * (double)iters * 8.0;
+        *outs[op] = ops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+} // namespace eucl

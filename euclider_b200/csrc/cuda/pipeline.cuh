@@ -1,0 +1,103 @@
+// Shared declarations of the wavefront pipeline: frame constants, the node arena and the launch
+// interface between api_device.cu (host orchestration) and kernels.cu (device code).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "euclider_b200.h"
+
+namespace eucl {
+
+// Per-frame constants.  The camera terms that need libm (tan, sqrt) are computed once on the
+// host in the reference's order (d3/entity/camera.rs:164-185, d4/entity/camera.rs:155-176);
+// the per-pixel part uses only IEEE add/mul/div/sqrt and is bit-reproducible on the device.
+struct FrameParams {
+    double location[EUCL_MAX_DIM];
+    double center[EUCL_MAX_DIM]; // location + forward * distance_from_screen_center
+    double up[EUCL_MAX_DIM];
+    double right[EUCL_MAX_DIM];
+    double time_millis; // (time * 1000).as_secs() / 1000.0
+    int32_t width, height;
+    int32_t max_depth;
+    int32_t _pad;
+};
+
+// Which rows of the frame one launch sequence covers.  A rank owns the bands b with
+// b % band_world == band_rank (band = band_rows consecutive rows); its rows are numbered
+// consecutively ("local rows") and processed in chunks of whole local rows.
+struct ChunkParams {
+    int32_t local_row0;  // first local row of this chunk
+    int32_t n_rows;      // rows in this chunk
+    int32_t band_rows, band_rank, band_world;
+    int32_t compact_rows; // 1: output row index = local row; 0: output row index = frame row
+    int32_t n_pixels;     // n_rows * width
+    int32_t _pad;
+};
+
+__host__ __device__ inline int frame_row_of_local(const ChunkParams& c, int local_row) {
+    if (c.band_world <= 1) return local_row;
+    int k = local_row / c.band_rows;
+    return (k * c.band_world + c.band_rank) * c.band_rows + local_row % c.band_rows;
+}
+
+// Ray-tree node record written by the shade kernel and consumed by the bottom-up resolve.
+struct NodeMeta {
+    double ratio;    // clamped reflection ratio
+    int32_t tchild;  // node id of the transmitted child, -1 if none
+    int32_t rchild;  // node id of the reflected child, -1 if none
+    uint32_t q;      // surface colour quantised to u8x4 (surface.rs:72), r | g<<8 | b<<16 | a<<24
+    uint32_t flags;
+};
+enum : uint32_t {
+    NODE_LEAF = 1u,      // `res` already holds the final colour of the node
+    NODE_HAS_SC = 2u,    // `res` holds the opaque surface colour (alpha quantises to 255): no transmitted child
+    NODE_FINAL_RGB = 4u, // level-0 checkerboard pixel: `res` is written out without compositing
+    NODE_UNDEFINED = 8u  // both branches None (the reference would panic): transparent black
+};
+
+// Node arena shared by all levels of one chunk: level l occupies node ids
+// [level_off[l], level_off[l] + count[l]).  Rays, hits, metadata and resolved colours are all
+// indexed by node id.  Planes of double2 give 128-bit coalesced loads/stores.
+struct Workspace {
+    int32_t capacity;   // nodes
+    int32_t _pad;
+    double2* ray_od;    // D planes of `capacity`: plane k = components (2k, 2k+1) of [origin, direction]
+    int32_t* ray_cur;   // entity the ray travels in; -1 = no ray (checkerboard pixel)
+    double2* hit_pn;    // D planes: [location, raw normal]
+    int2* hit_ei;       // (hit entity or -1, exiting)
+    NodeMeta* meta;
+    double2* res_rg;    // resolved colour, (r, g)
+    double2* res_ba;    // (b, a)
+    int32_t* count;     // [EUCL_MAX_LEVELS + 1] nodes per level
+    int32_t* level_off; // [EUCL_MAX_LEVELS + 1] first node id of each level
+    int32_t* overflow;  // set when a child could not be appended
+    int32_t* cam_entity; // material_at(camera location), -1 if none
+    unsigned long long* undefined_count;   // nodes that touched a corner the reference leaves undefined
+    unsigned long long* mega_level_counts; // [EUCL_MAX_LEVELS + 1] nodes per level, megakernel pipeline only
+};
+
+struct Launch {
+    cudaStream_t stream;
+    const uint8_t* blob;
+    size_t smem_bytes;
+    int grid_max; // upper bound on blocks for queue kernels
+};
+
+constexpr int kBlock = 128;
+
+// kernels.cu
+void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws);
+void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                   int32_t* hit_ids_out);
+void launch_intersect(int dim, const Launch& l, const Workspace& ws, int level);
+void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
+                  int32_t* hit_ids_out);
+void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level);
+void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                  uint8_t* out_rgb8);
+void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                       uint8_t* out_rgb8, int32_t* hit_ids_out);
+cudaError_t configure_kernels(size_t smem_bytes);
+int fp64_peak(double* dadd, double* dmul, double* dfma); // T op/s on the current device
+
+} // namespace eucl

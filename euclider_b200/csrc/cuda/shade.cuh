@@ -1,0 +1,505 @@
+// Shading on the device: ComposableSurface providers (surface.rs:201-542), palette colour
+// arithmetic, Perlin hue (d3/entity/surface.rs:22-40), mapped textures and LinearSpace material
+// transitions (material.rs:70-163).  Everything is f64 in the reference's operation order.
+#pragma once
+#include "intersect.cuh"
+
+namespace eucl {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kFracPi2 = 1.57079632679489661923132169163975144;
+constexpr double kApproxEpsilon = 1.0e-6; // nalgebra 0.8.2 approx_epsilon; the self-hit offset is (n * eps) * 128
+
+struct Rgba {
+    double r, g, b, a;
+};
+struct Pre { // palette PreAlpha<Rgb>
+    double r, g, b, a;
+};
+
+__device__ __forceinline__ double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+// palette to_pixel: clamp to [0,1], * 255, truncate.  A NaN channel (the reference would panic in
+// to_u8().unwrap()) is defined as 0, the same definition the oracle uses.
+__device__ __forceinline__ unsigned channel_to_u8(double c) {
+    if (isnan(c)) return 0u;
+    return (unsigned)(int)(clamp01(c) * 255.0);
+}
+__device__ __forceinline__ unsigned to_pixel4(const Rgba& c) {
+    return channel_to_u8(c.r) | (channel_to_u8(c.g) << 8) | (channel_to_u8(c.b) << 16) | (channel_to_u8(c.a) << 24);
+}
+__device__ __forceinline__ Rgba new_u8(unsigned q) {
+    return Rgba{(double)(q & 255u) / 255.0, (double)((q >> 8) & 255u) / 255.0, (double)((q >> 16) & 255u) / 255.0,
+                (double)(q >> 24) / 255.0};
+}
+__device__ __forceinline__ Pre into_premultiplied(const Rgba& c) {
+    double a = clamp01(c.a);
+    return Pre{c.r * a, c.g * a, c.b * a, a};
+}
+__device__ __forceinline__ bool is_normal(double a) { return isfinite(a) && fabs(a) >= 2.2250738585072014e-308; }
+__device__ __forceinline__ Rgba from_premultiplied(const Pre& p) {
+    double a = clamp01(p.a);
+    if (is_normal(a)) return Rgba{p.r / a, p.g / a, p.b / a, a};
+    return Rgba{0.0, 0.0, 0.0, a};
+}
+
+__device__ __forceinline__ double blend_channel(int fn, double a, double b, double sa, double da) {
+    switch (fn) {
+    case EUCL_BLEND_OVER: return a + b * (1.0 - sa);
+    case EUCL_BLEND_INSIDE: return a * da;
+    case EUCL_BLEND_OUTSIDE: return a * (1.0 - da);
+    case EUCL_BLEND_ATOP: return a * da + b * (1.0 - sa);
+    case EUCL_BLEND_XOR: return a * (1.0 - da) + b * (1.0 - sa);
+    case EUCL_BLEND_PLUS: return a + b;
+    case EUCL_BLEND_MULTIPLY: return a * b + a * (1.0 - da) + b * (1.0 - sa);
+    case EUCL_BLEND_SCREEN: return a + b - a * b;
+    case EUCL_BLEND_OVERLAY:
+        if (b * 2.0 <= da) return 2.0 * a * b + a * (1.0 - da) + b * (1.0 - sa);
+        return a * (1.0 + da) + b * (1.0 + sa) - 2.0 * a * b - da * sa;
+    case EUCL_BLEND_DARKEN: return fmin(a * da, b * sa) + a * (1.0 - da) + b * (1.0 - sa);
+    case EUCL_BLEND_LIGHTEN: return fmax(a * da, b * sa) + a * (1.0 - da) + b * (1.0 - sa);
+    case EUCL_BLEND_DODGE:
+        if (a == sa && !is_normal(b)) return a * (1.0 - da);
+        if (a == sa) return sa * da + a * (1.0 - da) + b * (1.0 - sa);
+        return sa * da * fmin(1.0, (b / da) * sa / (sa - a)) + a * (1.0 - da) + b * (1.0 - sa);
+    case EUCL_BLEND_BURN:
+        if (!is_normal(a) && b == da) return sa * da + b * (1.0 - sa);
+        if (!is_normal(a)) return b * (1.0 - sa);
+        return sa * da * (1.0 - fmin(1.0, (1.0 - b / da) * sa / a)) + a * (1.0 - da) + b * (1.0 - sa);
+    case EUCL_BLEND_HARD_LIGHT:
+        if (a * 2.0 <= sa) return 2.0 * a * b + a * (1.0 - da) + b * (1.0 - sa);
+        return a * (1.0 + da) + b * (1.0 + sa) - 2.0 * a * b - da * sa;
+    case EUCL_BLEND_SOFT_LIGHT: {
+        double m = is_normal(da) ? b / da : 0.0;
+        if (a * 2.0 <= sa) return b * (sa + (2.0 * a - sa) * (1.0 - m)) + a * (1.0 - da) + b * (1.0 - sa);
+        if (b * 4.0 <= da) {
+            double m2 = m * m, m3 = m2 * m;
+            return da * (2.0 * a - sa) * (m3 * 16.0 - m2 * 12.0 - m * 3.0) + a - a * da + b;
+        }
+        return da * (2.0 * a - sa) * (sqrt(m) - m) + a - a * da + b;
+    }
+    case EUCL_BLEND_DIFFERENCE: return a + b - 2.0 * fmin(a * da, b * sa);
+    case EUCL_BLEND_EXCLUSION: return a + b - 2.0 * a * b;
+    }
+    return a;
+}
+
+// palette Blend on premultiplied colours: `s` = self (source), `d` = argument (destination)
+__device__ __forceinline__ Pre blend_pre(int fn, const Pre& s, const Pre& d) {
+    const double sa = s.a, da = d.a;
+    double alpha;
+    switch (fn) {
+    case EUCL_BLEND_INSIDE: alpha = clamp01(sa * da); break;
+    case EUCL_BLEND_OUTSIDE: alpha = clamp01(sa * (1.0 - da)); break;
+    case EUCL_BLEND_ATOP: alpha = clamp01(da); break;
+    case EUCL_BLEND_XOR: alpha = clamp01(sa + da - 2.0 * sa * da); break;
+    case EUCL_BLEND_PLUS: alpha = clamp01(sa + da); break;
+    default: alpha = clamp01(sa + da - sa * da); break;
+    }
+    return Pre{blend_channel(fn, s.r, d.r, sa, da), blend_channel(fn, s.g, d.g, sa, da),
+               blend_channel(fn, s.b, d.b, sa, da), alpha};
+}
+__device__ __forceinline__ Pre over_pre(const Pre& s, const Pre& d) {
+    return Pre{s.r + d.r * (1.0 - s.a), s.g + d.g * (1.0 - s.a), s.b + d.b * (1.0 - s.a),
+               clamp01(s.a + d.a - s.a * d.a)};
+}
+
+// util.rs:265-285
+__device__ __forceinline__ Rgba combine_palette_color(const Rgba& a, const Rgba& b, double a_ratio) {
+    if (a_ratio <= 0.0) return b;
+    if (a_ratio >= 1.0) return a;
+    return Rgba{a.r * a_ratio + b.r * (1.0 - a_ratio), a.g * a_ratio + b.g * (1.0 - a_ratio),
+                a.b * a_ratio + b.b * (1.0 - a_ratio), a.a * a_ratio + b.a * (1.0 - a_ratio)};
+}
+
+// palette Hsv -> Rgb (hue in degrees), saturation = value = 1 at the only call site
+__device__ __forceinline__ Rgba hue_to_rgba(double hue_degrees) {
+    double deg = hue_degrees;
+    if (isfinite(deg)) {
+        while (deg >= 360.0) deg = deg - 360.0;
+        while (deg < 0.0) deg = deg + 360.0;
+    }
+    const double c = 1.0 * 1.0;
+    double h = deg / 60.0;
+    double x = c * (1.0 - fabs(fmod(h, 2.0) - 1.0));
+    double m = 1.0 - c;
+    double r, g, b;
+    if (h >= 0.0 && h < 1.0) { r = c; g = x; b = 0.0; }
+    else if (h >= 1.0 && h < 2.0) { r = x; g = c; b = 0.0; }
+    else if (h >= 2.0 && h < 3.0) { r = 0.0; g = c; b = x; }
+    else if (h >= 3.0 && h < 4.0) { r = 0.0; g = x; b = c; }
+    else if (h >= 4.0 && h < 5.0) { r = x; g = 0.0; b = c; }
+    else { r = c; g = 0.0; b = x; }
+    return Rgba{r + m, g + m, b + m, 1.0};
+}
+
+// noise 0.4.1 Perlin::get([f64; 4]) with the seed-0 permutation table staged in shared memory
+__device__ __forceinline__ double perlin4(const uint8_t* perm, const double point[4]) {
+    const double diag = 0.577350269189625764077083524672081875;
+    double near_d[4], far_d[4];
+    long long near_c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double f = floor(point[k]);
+        near_c[k] = (long long)f;
+        near_d[k] = point[k] - f;
+        far_d[k] = near_d[k] - 1.0;
+    }
+    double total = 0.0;
+#pragma unroll
+    for (int corner = 0; corner < 16; ++corner) {
+        double dd[4];
+        unsigned cc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool far = (corner >> k) & 1;
+            cc[k] = (unsigned)((far ? near_c[k] + 1 : near_c[k]) & 0xff);
+            dd[k] = far ? far_d[k] : near_d[k];
+        }
+        double attn = 1.0 - (((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]) + dd[3] * dd[3]);
+        double v = 0.0;
+        if (attn > 0.0) {
+            unsigned h = perm[cc[0]];
+            h = perm[h ^ cc[1]];
+            h = perm[h ^ cc[2]];
+            h = perm[h ^ cc[3]];
+            h &= 31u;
+            const unsigned zero_at = h >> 3, signs = h & 7u;
+            double g[4];
+            int bit = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((unsigned)k == zero_at) {
+                    g[k] = 0.0;
+                } else {
+                    g[k] = ((signs >> bit) & 1u) ? -diag : diag;
+                    ++bit;
+                }
+            }
+            double a2 = attn * attn;
+            v = (a2 * a2) * (((dd[0] * g[0] + dd[1] * g[1]) + dd[2] * g[2]) + dd[3] * g[3]);
+        }
+        total = corner == 0 ? v : total + v;
+    }
+    return total * 4.424369240215691;
+}
+
+// util.rs:287-299 on floats
+__device__ __forceinline__ double remainder_f(double a, double b) {
+    double rem = fmod(a, b);
+    if (rem == 0.0) return 0.0;
+    if (a < 0.0) return b + rem;
+    return rem;
+}
+__device__ __forceinline__ long long remainder_i(long long a, long long b) {
+    long long rem = a % b;
+    if (rem == 0) return 0;
+    if (a < 0) return b + rem;
+    return rem;
+}
+
+// One texel as 4 doubles in 0..255.  Out-of-domain coordinates (the reference would panic in
+// NumCast / get_pixel) fetch texel (0,0), the same definition the oracle uses.
+__device__ __forceinline__ Rgba fetch_texel(cudaTextureObject_t tex, const EuclTexture& t, double xf, double yf) {
+    long long x = 0, y = 0;
+    if ((xf > -1.0 && xf < 4294967296.0) && (yf > -1.0 && yf < 4294967296.0)) {
+        x = (long long)xf;
+        y = (long long)yf;
+    }
+    if (x >= (long long)t.width || y >= (long long)t.height) {
+        x = 0;
+        y = 0;
+    }
+    uchar4 px = tex2D<uchar4>(tex, (float)x + 0.5f, (float)y + 0.5f);
+    return Rgba{(double)px.x, (double)px.y, (double)px.z, (double)px.w};
+}
+
+// MappedTextureImpl::get_color with uv_sphere (+ uv_derank in 4-D) and the two image filters
+template <int D>
+__device__ __forceinline__ Rgba mapped_color(const SceneView& sv, int mapped, const Vec<D>& point) {
+    if (mapped < 0) return Rgba{0.0, 0.0, 0.0, 0.0}; // MappedTextureTransparent
+    const EuclMappedTexture mt = sv.mapped[mapped];
+    Vec<3> p;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
+    p = normalize(p);
+    const double u = 0.5 + atan2(p[1], p[0]) / (2.0 * kPi);
+    const double v = 0.5 - asin(p[2]) / kPi;
+    const EuclTexture t = sv.textures[mt.texture];
+    const cudaTextureObject_t tex = sv.tex_objects[mt.texture];
+    const double width = (double)t.width, height = (double)t.height;
+    if (mt.filter == EUCL_TEX_NEAREST) {
+        double x = floor(u * width), y = floor(v * height);
+        if (!((x > -1.0 && x < 4294967296.0) && (y > -1.0 && y < 4294967296.0))) {
+            x = 0.0;
+            y = 0.0;
+        }
+        long long xi = remainder_i((long long)x, (long long)t.width), yi = remainder_i((long long)y, (long long)t.height);
+        Rgba px = fetch_texel(tex, t, (double)xi, (double)yi);
+        return Rgba{px.r / 255.0, px.g / 255.0, px.b / 255.0, px.a / 255.0};
+    }
+    const double x = u * width - 0.5, y = v * height - 0.5;
+    const double fx = x - floor(x), fy = y - floor(y);
+    const double x0 = remainder_f(x + 0.0, width), x1 = remainder_f(x + 1.0, width);
+    const double y0 = remainder_f(y + 0.0, height), y1 = remainder_f(y + 1.0, height);
+    const Rgba p0 = fetch_texel(tex, t, x0, y0), p1 = fetch_texel(tex, t, x1, y0);
+    const Rgba p2 = fetch_texel(tex, t, x0, y1), p3 = fetch_texel(tex, t, x1, y1);
+    const double gx = 1.0 - fx, gy = 1.0 - fy;
+    return Rgba{((p0.r * gx + p1.r * fx) * gy + (p2.r * gx + p3.r * fx) * fy) / 255.0,
+                ((p0.g * gx + p1.g * fx) * gy + (p2.g * gx + p3.g * fx) * fy) / 255.0,
+                ((p0.b * gx + p1.b * fx) * gy + (p2.b * gx + p3.b * fx) * fy) / 255.0,
+                ((p0.a * gx + p1.a * fx) * gy + (p2.a * gx + p3.a * fx) * fy) / 255.0};
+}
+
+// --- materials ---------------------------------------------------------------------------------
+
+// meval-style RPN program (compiled on the host from the scene's expression strings)
+__device__ inline double eval_expr(const SceneView& sv, int first, int len, const double* vars) {
+    double st[16];
+    int sp = 0;
+    for (int i = first; i < first + len; ++i) {
+        const EuclExprOp o = sv.expr_ops[i];
+        if (o.op == EUCL_EX_CONST) {
+            st[sp++] = o.value;
+        } else if (o.op == EUCL_EX_VAR) {
+            st[sp++] = vars[o.arg];
+        } else if (o.op == EUCL_EX_NEG) {
+            st[sp - 1] = -st[sp - 1];
+        } else if (o.op == EUCL_EX_FUNC1) {
+            double x = st[sp - 1], r = x;
+            switch (o.arg) {
+            case EUCL_FN_SQRT: r = sqrt(x); break;
+            case EUCL_FN_ABS: r = fabs(x); break;
+            case EUCL_FN_EXP: r = exp(x); break;
+            case EUCL_FN_LN: r = log(x); break;
+            case EUCL_FN_SIN: r = sin(x); break;
+            case EUCL_FN_COS: r = cos(x); break;
+            case EUCL_FN_TAN: r = tan(x); break;
+            case EUCL_FN_ASIN: r = asin(x); break;
+            case EUCL_FN_ACOS: r = acos(x); break;
+            case EUCL_FN_ATAN: r = atan(x); break;
+            case EUCL_FN_SINH: r = sinh(x); break;
+            case EUCL_FN_COSH: r = cosh(x); break;
+            case EUCL_FN_TANH: r = tanh(x); break;
+            case EUCL_FN_FLOOR: r = floor(x); break;
+            case EUCL_FN_CEIL: r = ceil(x); break;
+            case EUCL_FN_ROUND: r = round(x); break;
+            case EUCL_FN_SIGNUM: r = rust_signum(x); break;
+            }
+            st[sp - 1] = r;
+        } else {
+            double b = st[--sp], a = st[sp - 1], r = 0.0;
+            switch (o.op) {
+            case EUCL_EX_ADD: r = a + b; break;
+            case EUCL_EX_SUB: r = a - b; break;
+            case EUCL_EX_MUL: r = a * b; break;
+            case EUCL_EX_DIV: r = a / b; break;
+            case EUCL_EX_REM: r = fmod(a, b); break;
+            case EUCL_EX_POW: r = pow(a, b); break;
+            case EUCL_EX_FUNC2:
+                if (o.arg == EUCL_FN_ATAN2) r = atan2(a, b);
+                else if (o.arg == EUCL_FN_MAX) r = fmax(a, b);
+                else r = fmin(a, b);
+                break;
+            }
+            st[sp - 1] = r;
+        }
+    }
+    return sp > 0 ? st[sp - 1] : 0.0;
+}
+
+// ComponentTransformation::transform_with (material.rs:91-112): all component expressions see the
+// same input vector
+template <int D>
+__device__ inline void apply_transform(const SceneView& sv, const EuclTransform& t, bool inverse, Vec<D>& v) {
+    double in[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) in[k] = v[k];
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        v[k] = inverse ? eval_expr(sv, t.inv_first[k], t.inv_len[k], in) : eval_expr(sv, t.fwd_first[k], t.fwd_len[k], in);
+}
+// Material::enter (Vacuum: no-op, material.rs:43-49; LinearSpace: forward transforms in order, :133-137)
+template <int D>
+__device__ __forceinline__ void material_enter(const SceneView& sv, int entity, Vec<D>& dir) {
+    const EuclMaterial m = sv.materials[sv.entities[entity].material];
+    if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
+    for (int k = 0; k < m.n_transforms; ++k) apply_transform<D>(sv, sv.transforms[m.transform_first + k], false, dir);
+}
+// Material::exit (LinearSpace: inverse transforms in reverse order, material.rs:139-142,156-162)
+template <int D>
+__device__ __forceinline__ void material_exit(const SceneView& sv, int entity, Vec<D>& dir) {
+    const EuclMaterial m = sv.materials[sv.entities[entity].material];
+    if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
+    for (int k = m.n_transforms - 1; k >= 0; --k) apply_transform<D>(sv, sv.transforms[m.transform_first + k], true, dir);
+}
+
+// --- surface providers -------------------------------------------------------------------------
+
+struct HitContext { // the fields of TracingContext (shape.rs:111-123) the providers read
+    int hit_entity;
+    bool exiting;
+};
+
+// util.rs:631-666: rotate `v` in the plane spanned by (self_, other) by `angle`
+template <int D>
+__device__ inline Vec<D> general_rotation(const Vec<D>& self_, const Vec<D>& other, double angle, const Vec<D>& v) {
+    double original[D][D], result[D][D]; // [row][col]
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) original[r][c] = r == c ? 1.0 : 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        original[r][0] = self_[r];
+        original[r][1] = other[r];
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) result[r][c] = original[r][c];
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            Vec<D> oc, rc;
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                oc[r] = original[r][i];
+                rc[r] = result[r][j];
+            }
+            Vec<D> upd = oc - rc * dot(rc, oc);
+#pragma unroll
+            for (int r = 0; r < D; ++r) original[r][i] = upd[r];
+        }
+        Vec<D> col;
+#pragma unroll
+        for (int r = 0; r < D; ++r) col[r] = original[r][i];
+        col = normalize(col);
+#pragma unroll
+        for (int r = 0; r < D; ++r) result[r][i] = col[r];
+    }
+    double rot[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) rot[r][c] = r == c ? 1.0 : 0.0;
+    const double ca = cos(angle), sa = sin(angle);
+    rot[0][0] = ca;
+    rot[0][1] = -sa;
+    rot[1][0] = sa;
+    rot[1][1] = ca;
+    // result * (rotation_matrix * result.transpose()); nalgebra accumulates from zero, so the
+    // multiplications by the identity part of `rot` are kept (0 * NaN must stay NaN)
+    double tmp[D][D], q[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc = acc + rot[i][k] * result[j][k];
+            tmp[i][j] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc = acc + result[i][k] * tmp[k][j];
+            q[i][j] = acc;
+        }
+    Vec<D> out;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = acc + v[j] * q[i][j];
+        out[i] = acc;
+    }
+    return out;
+}
+
+// reflection_ratio_uniform / reflection_ratio_fresnel (surface.rs:201-244), before clamping
+template <int D>
+__device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& normal_closer,
+                                                   bool exiting) {
+    if (sf.ratio_op == EUCL_RATIO_UNIFORM) return exiting ? 0.0 : sf.ratio_a;
+    const Vec<D> normal = -normal_closer;
+    const double from_theta = angle_between(dir, normal);
+    const double from_index = exiting ? sf.ratio_a : sf.ratio_b;
+    const double to_index = exiting ? sf.ratio_b : sf.ratio_a;
+    const double to_theta = asin((from_index / to_index) * sin(from_theta));
+    if (isnan(to_theta)) return 1.0;
+    const double cf = cos(from_theta), ct = cos(to_theta);
+    const double p1s = from_index * cf, p2s = to_index * ct;
+    const double p1p = from_index * ct, p2p = to_index * cf;
+    const double rs = (p1s - p2s) / (p1s + p2s);
+    const double rp = (p1p - p2p) / (p1p + p2p);
+    return (rs * rs + rp * rp) / (1.0 + 1.0);
+}
+
+// reflection_direction_specular (surface.rs:246-256)
+template <int D>
+__device__ __forceinline__ Vec<D> reflection_direction(const Vec<D>& dir, const Vec<D>& normal_closer) {
+    return normal_closer * -2.0 * dot(dir, normal_closer) + dir;
+}
+
+// threshold_direction_identity / threshold_direction_snell (surface.rs:259-288)
+template <int D>
+__device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& normal_closer,
+                                                      bool exiting) {
+    if (sf.thr_op == EUCL_THR_IDENTITY) return dir;
+    const Vec<D> normal = -normal_closer;
+    const double from_theta = angle_between(dir, normal);
+    const double modifier = exiting ? sf.thr_a : 1.0 / sf.thr_a;
+    const double to_theta = asin(modifier * sin(from_theta));
+    const double angle_delta = to_theta - from_theta;
+    return general_rotation<D>(normal, dir, angle_delta, dir);
+}
+
+// The surface colour program (postfix) of surface `sf` at a hit.
+template <int D>
+__device__ inline Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& location,
+                                     const Vec<D>& normal_raw, const Vec<D>& normal_closer, double time_millis) {
+    Rgba stack[8];
+    int sp = 0;
+    for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
+        const EuclColorOp& op = sv.color_ops[i];
+        const int code = op.op;
+        if (code == EUCL_COL_UNIFORM) { // surface.rs:425-429
+            stack[sp++] = Rgba{op.f[0], op.f[1], op.f[2], op.f[3]};
+        } else if (code == EUCL_COL_ILLUM_GLOBAL) { // surface.rs:410-422
+            const Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
+            const double original_angle = angle_between(normal_closer, dir);
+            const double angle = kPi - original_angle;
+            const double ratio = angle / kFracPi2;
+            stack[sp++] = combine_palette_color(dark, light, ratio);
+        } else if (code == EUCL_COL_ILLUM_DIR) { // surface.rs:392-408
+            const Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
+            Vec<D> light_direction;
+#pragma unroll
+            for (int k = 0; k < D; ++k) light_direction[k] = op.f[8 + k];
+            Vec<D> normal = normal_raw;
+            if (angle_between(dir, normal) > kFracPi2) normal = -normal;
+            const double angle = angle_between(normal, -light_direction);
+            const double ratio = 1.0 - angle / kPi;
+            stack[sp++] = combine_palette_color(dark, light, ratio);
+        } else if (code == EUCL_COL_PERLIN_HUE) { // d3/entity/surface.rs:22-40
+            const double size = op.f[0], speed = op.f[1];
+            const double point[4] = {location[0] / size, location[1] / size, location[2] / size, time_millis * speed};
+            stack[sp++] = hue_to_rgba(perlin4(sv.perlin, point) * 360.0);
+        } else if (code == EUCL_COL_TEXTURE) { // surface.rs:536-542
+            stack[sp++] = mapped_color<D>(sv, op.i0, location);
+        } else { // EUCL_COL_BLEND, surface.rs:295-307
+            const Rgba destination = stack[--sp];
+            const Rgba source = stack[--sp];
+            if (op.i0 == EUCL_BLEND_RATIO) stack[sp++] = combine_palette_color(source, destination, op.f[0]);
+            else stack[sp++] = from_premultiplied(blend_pre(op.i0, into_premultiplied(source), into_premultiplied(destination)));
+        }
+    }
+    return sp > 0 ? stack[sp - 1] : Rgba{0.0, 0.0, 0.0, 0.0};
+}
+
+} // namespace eucl
