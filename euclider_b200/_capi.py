@@ -89,7 +89,8 @@ class EuclFlatScene(C.Structure):
 class EuclRenderOpts(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("time_seconds", C.c_double),
                 ("band_rows", C.c_uint32), ("band_rank", C.c_uint32), ("band_world", C.c_uint32),
-                ("pipeline", C.c_int32), ("compact_rows", C.c_int32), ("want_hit_ids", C.c_int32)]
+                ("pipeline", C.c_int32), ("compact_rows", C.c_int32), ("want_hit_ids", C.c_int32),
+                ("profile", C.c_int32), ("_pad", C.c_int32)]
 
 
 class EuclStats(C.Structure):
@@ -131,6 +132,7 @@ PROTOTYPES = {
     "eucl_version": (C.c_char_p, []),
     "eucl_scene_create": (C.c_int, [C.POINTER(EuclFlatScene), C.c_int, C.POINTER(C.c_void_p)]),
     "eucl_scene_destroy": (None, [C.c_void_p]),
+    "eucl_scene_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eucl_band_rows_for_rank": (C.c_uint32, [C.POINTER(EuclRenderOpts)]),
     "eucl_render": (C.c_int, [C.c_void_p, C.POINTER(EuclCamera), C.POINTER(EuclRenderOpts), C.c_void_p, C.c_void_p,
                               C.POINTER(EuclStats)]),

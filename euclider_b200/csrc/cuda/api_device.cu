@@ -64,8 +64,10 @@ struct EuclScene {
     uint8_t* d_blob = nullptr;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> tex_objects;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // the stream kernels run on (own_stream unless the caller set one)
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_events; // per-launch events, profile mode only
     // workspace (grow-only)
     DeviceBuffer nodes;    // the node arena
     DeviceBuffer small;    // counters
@@ -177,7 +179,8 @@ void eucl_scene_destroy(EuclScene* s) {
     if (s->h_small) cudaFreeHost(s->h_small);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    for (auto& e : s->prof_events) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
 
@@ -212,7 +215,8 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                                \
     } while (0)
 
-    EUCL_CUDA_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    EUCL_CUDA_S(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
     EUCL_CUDA_S(cudaEventCreate(&s->ev[0]));
     EUCL_CUDA_S(cudaEventCreate(&s->ev[1]));
 
@@ -421,27 +425,53 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                 }
                 Workspace ws = carve(s, dim, s->arena_capacity);
                 EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));
+                // profile mode: one event after every launch; family = 0 raygen, 1 intersect, 2 shade, 3 resolve
+                std::vector<int> prof_family;
+                auto mark = [&](int family) {
+                    if (!o->profile) return;
+                    if (s->prof_events.size() <= prof_family.size()) {
+                        cudaEvent_t e = nullptr;
+                        cudaEventCreate(&e);
+                        s->prof_events.push_back(e);
+                    }
+                    cudaEventRecord(s->prof_events[prof_family.size()], s->stream);
+                    prof_family.push_back(family);
+                };
+                mark(-1);
                 launch_camera_entity(dim, l, fp, ws);
                 st.launches += 1;
                 if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) {
                     if (cam->max_depth > 24) return fail(EUCL_ERR_SCENE_LIMIT, "megakernel pipeline supports max_depth <= 24");
                     launch_megakernel(dim, l, fp, cp, ws, d_rgb, d_hit);
+                    mark(1);
                     st.launches += 1;
                 } else {
                     launch_raygen(dim, l, fp, cp, ws, d_hit);
+                    mark(0);
                     for (int level = 0; level < (int)cam->max_depth; ++level) {
                         launch_intersect(dim, l, ws, level);
+                        mark(1);
                         launch_shade(dim, l, fp, cp, ws, level, d_hit);
+                        mark(2);
                     }
                     launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
+                    mark(2);
                     for (int level = (int)cam->max_depth - 1; level >= 1; --level) launch_resolve(dim, l, ws, level);
                     launch_final(dim, l, fp, cp, ws, d_rgb);
+                    mark(3);
                     st.launches += 3 + 2 * cam->max_depth + (cam->max_depth > 0 ? cam->max_depth - 1 : 0);
                 }
                 EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
                                           s->stream));
                 EUCL_CUDA(cudaStreamSynchronize(s->stream));
                 EUCL_CUDA(cudaGetLastError());
+                for (size_t k = 1; k < prof_family.size(); ++k) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, s->prof_events[k - 1], s->prof_events[k]);
+                    float* slot = prof_family[k] == 0 ? &st.ms_raygen : prof_family[k] == 1 ? &st.ms_intersect
+                                  : prof_family[k] == 2 ? &st.ms_shade : &st.ms_resolve;
+                    *slot += ms;
+                }
                 if (s->h_small[SmallLayout::overflow]) {
                     // levels after the overflowing one were skipped, so the counts are a lower bound only
                     long long need = 0;
@@ -520,6 +550,14 @@ int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     EUCL_CUDA(cudaMemcpyAsync(out_rgb8, s->frame.ptr, pixels * 3, cudaMemcpyDeviceToHost, s->stream));
     if (want_hit) EUCL_CUDA(cudaMemcpyAsync(out_hit_ids, s->hit_ids.ptr, pixels * 4, cudaMemcpyDeviceToHost, s->stream));
     EUCL_CUDA(cudaStreamSynchronize(s->stream));
+    return EUCL_OK;
+}
+
+int eucl_scene_set_stream(EuclScene* s, void* cuda_stream) {
+    if (!s) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_set_stream: null scene");
+    EUCL_CUDA(cudaSetDevice(s->device));
+    EUCL_CUDA(cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
     return EUCL_OK;
 }
 

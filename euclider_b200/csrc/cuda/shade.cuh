@@ -223,8 +223,8 @@ __device__ __forceinline__ Rgba mapped_color(const SceneView& sv, int mapped, co
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
     p = normalize(p);
-    const double u = 0.5 + atan2(p[1], p[0]) / (2.0 * kPi);
-    const double v = 0.5 - asin(p[2]) / kPi;
+    const double u = 0.5 + eucl_det::det_atan2(p[1], p[0]) / (2.0 * kPi);
+    const double v = 0.5 - eucl_det::det_asin(p[2]) / kPi;
     const EuclTexture t = sv.textures[mt.texture];
     const cudaTextureObject_t tex = sv.tex_objects[mt.texture];
     const double width = (double)t.width, height = (double)t.height;
@@ -272,12 +272,12 @@ __device__ inline double eval_expr(const SceneView& sv, int first, int len, cons
             case EUCL_FN_ABS: r = fabs(x); break;
             case EUCL_FN_EXP: r = exp(x); break;
             case EUCL_FN_LN: r = log(x); break;
-            case EUCL_FN_SIN: r = sin(x); break;
-            case EUCL_FN_COS: r = cos(x); break;
+            case EUCL_FN_SIN: r = eucl_det::det_sin(x); break;
+            case EUCL_FN_COS: r = eucl_det::det_cos(x); break;
             case EUCL_FN_TAN: r = tan(x); break;
-            case EUCL_FN_ASIN: r = asin(x); break;
-            case EUCL_FN_ACOS: r = acos(x); break;
-            case EUCL_FN_ATAN: r = atan(x); break;
+            case EUCL_FN_ASIN: r = eucl_det::det_asin(x); break;
+            case EUCL_FN_ACOS: r = eucl_det::det_acos(x); break;
+            case EUCL_FN_ATAN: r = eucl_det::det_atan(x); break;
             case EUCL_FN_SINH: r = sinh(x); break;
             case EUCL_FN_COSH: r = cosh(x); break;
             case EUCL_FN_TANH: r = tanh(x); break;
@@ -297,7 +297,7 @@ __device__ inline double eval_expr(const SceneView& sv, int first, int len, cons
             case EUCL_EX_REM: r = fmod(a, b); break;
             case EUCL_EX_POW: r = pow(a, b); break;
             case EUCL_EX_FUNC2:
-                if (o.arg == EUCL_FN_ATAN2) r = atan2(a, b);
+                if (o.arg == EUCL_FN_ATAN2) r = eucl_det::det_atan2(a, b);
                 else if (o.arg == EUCL_FN_MAX) r = fmax(a, b);
                 else r = fmin(a, b);
                 break;
@@ -384,7 +384,7 @@ __device__ inline Vec<D> general_rotation(const Vec<D>& self_, const Vec<D>& oth
     for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = 0; c < D; ++c) rot[r][c] = r == c ? 1.0 : 0.0;
-    const double ca = cos(angle), sa = sin(angle);
+    const double ca = eucl_det::det_cos(angle), sa = eucl_det::det_sin(angle);
     rot[0][0] = ca;
     rot[0][1] = -sa;
     rot[1][0] = sa;
@@ -430,9 +430,9 @@ __device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, const 
     const double from_theta = angle_between(dir, normal);
     const double from_index = exiting ? sf.ratio_a : sf.ratio_b;
     const double to_index = exiting ? sf.ratio_b : sf.ratio_a;
-    const double to_theta = asin((from_index / to_index) * sin(from_theta));
+    const double to_theta = eucl_det::det_asin((from_index / to_index) * eucl_det::det_sin(from_theta));
     if (isnan(to_theta)) return 1.0;
-    const double cf = cos(from_theta), ct = cos(to_theta);
+    const double cf = eucl_det::det_cos(from_theta), ct = eucl_det::det_cos(to_theta);
     const double p1s = from_index * cf, p2s = to_index * ct;
     const double p1p = from_index * ct, p2p = to_index * cf;
     const double rs = (p1s - p2s) / (p1s + p2s);
@@ -454,7 +454,7 @@ __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, con
     const Vec<D> normal = -normal_closer;
     const double from_theta = angle_between(dir, normal);
     const double modifier = exiting ? sf.thr_a : 1.0 / sf.thr_a;
-    const double to_theta = asin(modifier * sin(from_theta));
+    const double to_theta = eucl_det::det_asin(modifier * eucl_det::det_sin(from_theta));
     const double angle_delta = to_theta - from_theta;
     return general_rotation<D>(normal, dir, angle_delta, dir);
 }

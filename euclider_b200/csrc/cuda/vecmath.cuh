@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "eucl_detmath.h"
+
 namespace eucl {
 
 template <int D>
@@ -70,7 +72,7 @@ __device__ __forceinline__ double angle_cos(const Vec<D>& a, const Vec<D>& b) {
     return dot(a, b) / (norm(a) * norm(b));
 }
 __device__ __forceinline__ double angle_from_cos(double c) {
-    double r = acos(c);
+    double r = eucl_det::det_acos(c); // deterministic libm shared with the oracle (include/eucl_detmath.h)
     return isnan(r) ? 0.0 : r;
 }
 template <int D>

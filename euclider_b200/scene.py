@@ -86,7 +86,8 @@ class Environment:
 
     def render(self, dimensions: Tuple[int, int], time: float = 0.0, threads: int = 0,
                context: Optional[SimulationContext] = None, *, device: int = 0, want_hit_ids: bool = False,
-               band_rows: int = 0, band_rank: int = 0, band_world: int = 1, out: Optional[np.ndarray] = None) -> RawImage2d:
+               band_rows: int = 0, band_rank: int = 0, band_world: int = 1, out: Optional[np.ndarray] = None,
+               profile: bool = False) -> RawImage2d:
         """Environment::render.  `time` is seconds since start (the reference passes a Duration);
         `threads` is accepted for signature parity and ignored (the GPU schedules the pixels)."""
         del threads
@@ -94,7 +95,7 @@ class Environment:
         width, height = int(dimensions[0]) // context.resolution, int(dimensions[1]) // context.resolution
         opts = EuclRenderOpts(width=width, height=height, time_seconds=float(time), band_rows=band_rows,
                               band_rank=band_rank, band_world=band_world, pipeline=self.pipeline, compact_rows=0,
-                              want_hit_ids=int(want_hit_ids))
+                              want_hit_ids=int(want_hit_ids), profile=int(profile))
         if out is None:
             out = np.zeros((height, width, 3), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.size == height * width * 3 and out.flags["C_CONTIGUOUS"]
@@ -107,11 +108,12 @@ class Environment:
     # -- device-resident variant (inputs and outputs stay in HBM) --------------------------------
     def render_device(self, d_out_rgb8: int, dimensions: Tuple[int, int], time: float = 0.0, *, device: int = 0,
                       d_out_hit_ids: int = 0, band_rows: int = 0, band_rank: int = 0, band_world: int = 1,
-                      compact_rows: bool = False) -> dict:
+                      compact_rows: bool = False, profile: bool = False) -> dict:
         width, height = int(dimensions[0]), int(dimensions[1])
         opts = EuclRenderOpts(width=width, height=height, time_seconds=float(time), band_rows=band_rows,
                               band_rank=band_rank, band_world=band_world, pipeline=self.pipeline,
-                              compact_rows=int(compact_rows), want_hit_ids=int(bool(d_out_hit_ids)))
+                              compact_rows=int(compact_rows), want_hit_ids=int(bool(d_out_hit_ids)),
+                              profile=int(profile))
         stats = EuclStats()
         check(lib().eucl_render_device(self._device_scene(device), C.byref(self.camera), C.byref(opts),
                                        C.c_void_p(d_out_rgb8), C.c_void_p(d_out_hit_ids) if d_out_hit_ids else None,
@@ -133,6 +135,10 @@ class Environment:
             check(lib().eucl_scene_create(lib().eucl_parsed_flat(self._parsed), device, C.byref(handle)))
             self._scenes[device] = handle
         return self._scenes[device]
+
+    def set_stream(self, cuda_stream: int, device: int = 0) -> None:
+        """Runs this environment's kernels on `cuda_stream` (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(lib().eucl_scene_set_stream(self._device_scene(device), C.c_void_p(cuda_stream)))
 
     def close(self) -> None:
         for handle in self._scenes.values():

@@ -264,6 +264,8 @@ typedef struct EuclRenderOpts {
     int32_t compact_rows;   /* 0: rows land at their frame position (buffer = full frame)
                                1: this rank's rows are packed contiguously in band order */
     int32_t want_hit_ids;   /* also write the primary-ray hit-entity id map */
+    int32_t profile;        /* 1: record per-kernel-family device times into EuclStats (adds events) */
+    int32_t _pad;
 } EuclRenderOpts;
 
 typedef struct EuclStats {
@@ -286,6 +288,10 @@ const char* eucl_version(void);
 /* The flat scene is borrowed for the duration of the call only. */
 int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out);
 void eucl_scene_destroy(EuclScene* scene);
+
+/* Run this scene's kernels on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
+ * stream) instead of the scene's own; NULL restores the private stream. */
+int eucl_scene_set_stream(EuclScene* scene, void* cuda_stream);
 
 /* Number of rows / bytes this rank's share of a frame occupies (compact layout). */
 uint32_t eucl_band_rows_for_rank(const EuclRenderOpts* opts);

@@ -27,8 +27,32 @@
 #include <vector>
 
 #include "euclider_b200.h"
+#include "eucl_detmath.h"
 
 namespace {
+
+// Transcendental functions.  The reference calls the platform libm through Rust's std (f64::acos
+// ...).  Two builds of this oracle exist:
+//   liboracle.so      (default)           : the host's glibc -- what the Rust binary would link here
+//   liboracle_det.so  (-DORACLE_DETMATH)  : include/eucl_detmath.h, the fdlibm-style libm the CUDA
+//                                           path uses, for BIT-EXACT comparison with the GPU
+namespace om {
+#ifdef ORACLE_DETMATH
+inline double acos(double x) { return eucl_det::det_acos(x); }
+inline double asin(double x) { return eucl_det::det_asin(x); }
+inline double sin(double x) { return eucl_det::det_sin(x); }
+inline double cos(double x) { return eucl_det::det_cos(x); }
+inline double atan(double x) { return eucl_det::det_atan(x); }
+inline double atan2(double y, double x) { return eucl_det::det_atan2(y, x); }
+#else
+inline double acos(double x) { return std::acos(x); }
+inline double asin(double x) { return std::asin(x); }
+inline double sin(double x) { return std::sin(x); }
+inline double cos(double x) { return std::cos(x); }
+inline double atan(double x) { return std::atan(x); }
+inline double atan2(double y, double x) { return std::atan2(y, x); }
+#endif
+} // namespace om
 
 constexpr double PI = 3.14159265358979323846264338327950288;     // BaseFloat::pi()
 constexpr double FRAC_PI_2 = 1.57079632679489661923132169163975144; // BaseFloat::frac_pi_2()
@@ -95,7 +119,7 @@ Vec<D> normalize(const Vec<D>& a) { return a / norm(a); }
 // util.rs:712-722
 template <int D>
 double angle_between(const Vec<D>& a, const Vec<D>& b) {
-    double result = std::acos(dot(a, b) / (norm(a) * norm(b)));
+    double result = om::acos(dot(a, b) / (norm(a) * norm(b)));
     return std::isnan(result) ? 0.0 : result;
 }
 
@@ -682,12 +706,12 @@ struct Tracer {
                 case EUCL_FN_ABS: r = std::fabs(x); break;
                 case EUCL_FN_EXP: r = std::exp(x); break;
                 case EUCL_FN_LN: r = std::log(x); break;
-                case EUCL_FN_SIN: r = std::sin(x); break;
-                case EUCL_FN_COS: r = std::cos(x); break;
+                case EUCL_FN_SIN: r = om::sin(x); break;
+                case EUCL_FN_COS: r = om::cos(x); break;
                 case EUCL_FN_TAN: r = std::tan(x); break;
-                case EUCL_FN_ASIN: r = std::asin(x); break;
-                case EUCL_FN_ACOS: r = std::acos(x); break;
-                case EUCL_FN_ATAN: r = std::atan(x); break;
+                case EUCL_FN_ASIN: r = om::asin(x); break;
+                case EUCL_FN_ACOS: r = om::acos(x); break;
+                case EUCL_FN_ATAN: r = om::atan(x); break;
                 case EUCL_FN_SINH: r = std::sinh(x); break;
                 case EUCL_FN_COSH: r = std::cosh(x); break;
                 case EUCL_FN_TANH: r = std::tanh(x); break;
@@ -709,7 +733,7 @@ struct Tracer {
                 case EUCL_EX_REM: r = std::fmod(a, b); break;
                 case EUCL_EX_POW: r = std::pow(a, b); break;
                 case EUCL_EX_FUNC2:
-                    if (o.arg == EUCL_FN_ATAN2) r = std::atan2(a, b);
+                    if (o.arg == EUCL_FN_ATAN2) r = om::atan2(a, b);
                     else if (o.arg == EUCL_FN_MAX) r = std::fmax(a, b);
                     else r = std::fmin(a, b);
                     break;
@@ -799,8 +823,8 @@ struct Tracer {
         Vec<3> p;
         for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
         p = normalize(p);
-        double u = 0.5 + std::atan2(p[1], p[0]) / (2.0 * PI);
-        double v = 0.5 - std::asin(p[2]) / PI;
+        double u = 0.5 + om::atan2(p[1], p[0]) / (2.0 * PI);
+        double v = 0.5 - om::asin(p[2]) / PI;
         return sample_texture(mt, u, v);
     }
 
@@ -842,10 +866,10 @@ struct Tracer {
         double rot[D][D];
         for (int r = 0; r < D; ++r)
             for (int c = 0; c < D; ++c) rot[r][c] = r == c ? 1.0 : 0.0;
-        rot[0][0] = std::cos(angle);
-        rot[0][1] = -std::sin(angle);
-        rot[1][0] = std::sin(angle);
-        rot[1][1] = std::cos(angle);
+        rot[0][0] = om::cos(angle);
+        rot[0][1] = -om::sin(angle);
+        rot[1][0] = om::sin(angle);
+        rot[1][1] = om::cos(angle);
         // result * (rotation_matrix * result.transpose()); nalgebra accumulates from zero
         double tmp[D][D], q[D][D];
         for (int i = 0; i < D; ++i)
@@ -876,12 +900,12 @@ struct Tracer {
         double from_theta = angle_between(c.direction, normal);
         double from_index = c.exiting ? sf.ratio_a : sf.ratio_b;
         double to_index = c.exiting ? sf.ratio_b : sf.ratio_a;
-        double to_theta = std::asin((from_index / to_index) * std::sin(from_theta));
+        double to_theta = om::asin((from_index / to_index) * om::sin(from_theta));
         if (std::isnan(to_theta)) return 1.0;
-        double product_1_s = from_index * std::cos(from_theta);
-        double product_2_s = to_index * std::cos(to_theta);
-        double product_1_p = from_index * std::cos(to_theta);
-        double product_2_p = to_index * std::cos(from_theta);
+        double product_1_s = from_index * om::cos(from_theta);
+        double product_2_s = to_index * om::cos(to_theta);
+        double product_1_p = from_index * om::cos(to_theta);
+        double product_2_p = to_index * om::cos(from_theta);
         double rs = (product_1_s - product_2_s) / (product_1_s + product_2_s);
         double rp = (product_1_p - product_2_p) / (product_1_p + product_2_p);
         double reflectance_s = rs * rs, reflectance_p = rp * rp;
@@ -896,7 +920,7 @@ struct Tracer {
         Vec<D> normal = -c.normal_closer;
         double from_theta = angle_between(c.direction, normal);
         double modifier = c.exiting ? sf.thr_a : 1.0 / sf.thr_a;
-        double to_theta = std::asin(modifier * std::sin(from_theta));
+        double to_theta = om::asin(modifier * om::sin(from_theta));
         double angle_delta = to_theta - from_theta;
         return general_rotation(normal, c.direction, angle_delta, c.direction);
     }
@@ -1269,6 +1293,29 @@ void oracle_to_pixel(const double* rgba, uint8_t* out) {
 }
 
 double oracle_perlin4(const uint8_t* perm, const double* point) { return perlin4(perm, point); }
+
+// eucl_detmath functions (present in both builds), fn: 0 acos, 1 asin, 2 sin, 3 cos, 4 atan
+void oracle_detmath_unary(int fn, const double* x, double* out, int n) {
+    for (int i = 0; i < n; ++i) {
+        switch (fn) {
+        case 0: out[i] = eucl_det::det_acos(x[i]); break;
+        case 1: out[i] = eucl_det::det_asin(x[i]); break;
+        case 2: out[i] = eucl_det::det_sin(x[i]); break;
+        case 3: out[i] = eucl_det::det_cos(x[i]); break;
+        default: out[i] = eucl_det::det_atan(x[i]); break;
+        }
+    }
+}
+void oracle_detmath_atan2(const double* y, const double* x, double* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = eucl_det::det_atan2(y[i], x[i]);
+}
+int oracle_uses_detmath(void) {
+#ifdef ORACLE_DETMATH
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 void oracle_hsv_to_rgb(double h, double s, double v, double* rgb) { hsv_to_rgb(h, s, v, rgb); }
 

@@ -15,24 +15,25 @@ from euclider_b200._capi import EUCL_MAX_LEVELS, EuclCamera, EuclFlatScene, Eucl
 
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
-LIB_PATH = ORACLE_DIR / "liboracle.so"
-_lib = None
+LIB_PATHS = {"glibc": ORACLE_DIR / "liboracle.so", "det": ORACLE_DIR / "liboracle_det.so"}
+_libs = {}
 
 dptr = C.POINTER(C.c_double)
 
 
-def build() -> Path:
-    subprocess.run(["make", "-C", str(ORACLE_DIR), "liboracle.so"], check=True, capture_output=True)
-    return LIB_PATH
+def build() -> None:
+    subprocess.run(["make", "-C", str(ORACLE_DIR), "all"], check=True, capture_output=True)
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        src_mtime = max((ORACLE_DIR / "oracle.cc").stat().st_mtime, (ROOT / "include" / "euclider_b200.h").stat().st_mtime)
-        if not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src_mtime:
+def lib(variant: str = "det") -> C.CDLL:
+    """variant "det": transcendental functions from include/eucl_detmath.h (bit-comparable with the
+    CUDA path); "glibc": the host libm (what the Rust reference would link on this platform)."""
+    if variant not in _libs:
+        path = LIB_PATHS[variant]
+        deps = [ORACLE_DIR / "oracle.cc", ROOT / "include" / "euclider_b200.h", ROOT / "include" / "eucl_detmath.h"]
+        if not path.exists() or path.stat().st_mtime < max(d.stat().st_mtime for d in deps):
             build()
-        h = C.CDLL(str(LIB_PATH))
+        h = C.CDLL(str(path))
         h.oracle_render.restype = C.c_int
         h.oracle_render.argtypes = [C.POINTER(EuclFlatScene), C.POINTER(EuclCamera), C.c_uint32, C.c_uint32, C.c_double,
                                     C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -76,8 +77,13 @@ def lib() -> C.CDLL:
         h.oracle_ray_vector.restype = None
         h.oracle_ray_vector.argtypes = [C.POINTER(EuclFlatScene), C.POINTER(EuclCamera), C.c_int, C.c_int, C.c_int,
                                         C.c_int, dptr]
-        _lib = h
-    return _lib
+        h.oracle_detmath_unary.restype = None
+        h.oracle_detmath_unary.argtypes = [C.c_int, dptr, dptr, C.c_int]
+        h.oracle_detmath_atan2.restype = None
+        h.oracle_detmath_atan2.argtypes = [dptr, dptr, dptr, C.c_int]
+        h.oracle_uses_detmath.restype = C.c_int
+        _libs[variant] = h
+    return _libs[variant]
 
 
 def darr(values):
@@ -85,7 +91,8 @@ def darr(values):
     return (C.c_double * len(values))(*values)
 
 
-def render(env, width: int, height: int, time: float = 0.0, threads: int | None = None, rows=None, camera=None):
+def render(env, width: int, height: int, time: float = 0.0, threads: int | None = None, rows=None, camera=None,
+           variant: str = "det"):
     """Oracle frame for an euclider_b200.Environment: (rgb uint8 [rows,w,3], hit int32 [rows,w], stats dict)."""
     threads = threads or os.cpu_count() or 1
     r0, r1 = rows if rows is not None else (0, height)
@@ -94,7 +101,7 @@ def render(env, width: int, height: int, time: float = 0.0, threads: int | None 
     stats = np.zeros(8 + EUCL_MAX_LEVELS, dtype=np.uint64)
     cam = camera if camera is not None else env.camera
     flat = env.flat
-    rc = lib().oracle_render(C.byref(flat), C.byref(cam), width, height, float(time), r0, r1, threads,
+    rc = lib(variant).oracle_render(C.byref(flat), C.byref(cam), width, height, float(time), r0, r1, threads,
                              rgb.ctypes.data, hit.ctypes.data, stats.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"oracle_render failed: {rc}")

@@ -35,16 +35,21 @@ def main():
     for name in args.scenes:
         env = eb.load_reference_scene(name)
         t0 = time.time()
-        ref_rgb, ref_hit, ref_stats = oracle_api.render(env, args.width, args.height, time=1.234)
+        ref_rgb, ref_hit, ref_stats = oracle_api.render(env, args.width, args.height, time=1.234, variant="det")
         t_cpu = time.time() - t0
-        entry = {"oracle_s": t_cpu, "oracle_stats": ref_stats}
+        gl_rgb, gl_hit, gl_stats = oracle_api.render(env, args.width, args.height, time=1.234, variant="glibc")
+        entry = {"oracle_s": t_cpu, "oracle_stats": ref_stats, "glibc_stats": gl_stats}
         for pipe_name, pipe in (("wavefront", eb.EUCL_PIPELINE_WAVEFRONT), ("megakernel", eb.EUCL_PIPELINE_MEGAKERNEL)):
             env.pipeline = pipe
             img = env.render((args.width, args.height), time=1.234, want_hit_ids=True)
             img = env.render((args.width, args.height), time=1.234, want_hit_ids=True)
             exact, within1, maxdiff = compare(img.data, ref_rgb)
             hit_same = float((img.hit_ids == ref_hit).mean())
+            g_exact, g_within1, g_maxdiff = compare(img.data, gl_rgb)
             entry[pipe_name] = {"exact": exact, "within1": within1, "maxdiff": maxdiff, "hit_same": hit_same,
+                                "glibc_exact": g_exact, "glibc_within1": g_within1, "glibc_maxdiff": g_maxdiff,
+                                "glibc_hit_same": float((img.hit_ids == gl_hit).mean()),
+                                "levels_match": img.stats["level_counts"] == ref_stats["level_counts"],
                                 "segments": img.stats["segments"], "level_counts": img.stats["level_counts"],
                                 "ms_total": img.stats["ms_total"], "retries": img.stats["retries"],
                                 "segments_match": img.stats["segments"] == ref_stats["segments"]}

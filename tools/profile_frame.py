@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Renders a few device-resident frames of one scene: the command profiled under ncu."""
+import argparse
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+import euclider_b200 as eb  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scene", default="3d_room")
+ap.add_argument("--width", type=int, default=3840)
+ap.add_argument("--height", type=int, default=2160)
+ap.add_argument("--frames", type=int, default=2)
+ap.add_argument("--pipeline", default="wavefront")
+args = ap.parse_args()
+env = eb.load_reference_scene(args.scene)
+env.pipeline = eb.EUCL_PIPELINE_MEGAKERNEL if args.pipeline == "megakernel" else eb.EUCL_PIPELINE_WAVEFRONT
+out = torch.empty((args.height, args.width, 3), dtype=torch.uint8, device="cuda")
+for i in range(args.frames):
+    st = env.render_device(out.data_ptr(), (args.width, args.height), 0.0, profile=(i == args.frames - 1))
+print({k: st[k] for k in ("segments", "launches", "ms_total", "ms_intersect", "ms_shade", "ms_resolve", "level_counts")})
