@@ -485,7 +485,9 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                 break;
             }
             st.pixels += (uint64_t)cp.n_pixels;
-            for (uint32_t lv = 0; lv <= cam->max_depth; ++lv) {
+            // camera in no entity: checkerboard pixels, Universe::trace is never called (mod.rs:385-396)
+            const bool traced = s->h_small[SmallLayout::cam_entity] >= 0;
+            for (uint32_t lv = 0; traced && lv <= cam->max_depth; ++lv) {
                 uint64_t c = o->pipeline == EUCL_PIPELINE_MEGAKERNEL
                                  ? ((const unsigned long long*)(s->h_small + SmallLayout::mega64))[lv]
                                  : (uint64_t)s->h_small[SmallLayout::count + lv];

@@ -136,6 +136,12 @@ class Environment:
             self._scenes[device] = handle
         return self._scenes[device]
 
+    def set_texture(self, slot: int, width: int, height: int, rgba8: bytes) -> None:
+        """Fills texture slot `slot` with decoded RGBA8 pixels (row 0 = top); for callers that decode
+        images themselves.  Must happen before the first render."""
+        assert len(rgba8) == width * height * 4
+        check(lib().eucl_parsed_set_texture(self._parsed, slot, width, height, rgba8))
+
     def set_stream(self, cuda_stream: int, device: int = 0) -> None:
         """Runs this environment's kernels on `cuda_stream` (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(lib().eucl_scene_set_stream(self._device_scene(device), C.c_void_p(cuda_stream)))
