@@ -95,7 +95,7 @@ static_assert(SmallLayout::total <= kSmallInts, "small buffer layout");
 
 size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
-// Leaves / hits a CSG program can hold, to validate against the per-thread arena (intersect.cuh)
+// Structural validation of the post-order CSG programs of a flat scene.
 int validate_programs(const EuclFlatScene& f, std::string* why) {
     for (int e = 0; e < f.n_entities; ++e) {
         const EuclEntity& ent = f.entities[e];
@@ -103,7 +103,7 @@ int validate_programs(const EuclFlatScene& f, std::string* why) {
             *why = "entity " + std::to_string(e) + ": node range out of bounds";
             return EUCL_ERR_INVALID_ARGUMENT;
         }
-        int leaf_hits = 0, depth = 0, max_depth = 0;
+        int depth = 0;
         for (int n = ent.node_first; n <= ent.node_root; ++n) {
             const EuclNode& nd = f.nodes[n];
             if (nd.op == EUCL_CSG_LEAF) {
@@ -111,31 +111,115 @@ int validate_programs(const EuclFlatScene& f, std::string* why) {
                     *why = "node " + std::to_string(n) + ": primitive index out of bounds";
                     return EUCL_ERR_INVALID_ARGUMENT;
                 }
-                int k = f.prims[nd.prim].kind;
-                leaf_hits += (k == EUCL_PRIM_SPHERE || k == EUCL_PRIM_CYLINDER) ? 2 : 1;
                 ++depth;
             } else {
-                if (depth < 2 || nd.first < ent.node_first || nd.first >= n) {
+                if (nd.op < EUCL_CSG_UNION || nd.op > EUCL_CSG_SYMDIFF || depth < 2 || nd.first < ent.node_first ||
+                    nd.first >= n) {
                     *why = "node " + std::to_string(n) + ": malformed post-order program";
                     return EUCL_ERR_INVALID_ARGUMENT;
                 }
                 --depth;
             }
-            max_depth = std::max(max_depth, depth);
         }
         if (depth != 1) {
             *why = "entity " + std::to_string(e) + ": CSG program does not reduce to one shape";
             return EUCL_ERR_INVALID_ARGUMENT;
         }
-        // live lists (<= leaf_hits) + one merge output (<= leaf_hits + 2)
-        if (2 * leaf_hits + 2 > CSG_ARENA || max_depth > CSG_LIST_STACK || ent.node_root - ent.node_first + 1 > 64 * 4) {
-            *why = "entity " + std::to_string(e) + ": CSG program too large for the device evaluator (" +
-                   std::to_string(leaf_hits) + " leaf hits, nesting " + std::to_string(max_depth) + ")";
-            return EUCL_ERR_SCENE_LIMIT;
-        }
     }
     return EUCL_OK;
 }
+
+// Rewrites the binary post-order programs into macro programs (intersect.cuh): maximal left folds
+// of leaves under Union / Intersection become one M_CHAIN node.
+struct MacroBuilder {
+    const EuclFlatScene& f;
+    std::vector<MNode> out;
+    static constexpr int kMaxChain = CHAIN_ROOT_CAP / 2;
+
+    int hits_of_prim(int prim) const {
+        const int k = f.prims[prim].kind;
+        return (k == EUCL_PRIM_SPHERE || k == EUCL_PRIM_CYLINDER) ? 2 : (k == EUCL_PRIM_VOID ? 0 : 1);
+    }
+    int child_b(int n) const { return n - 1; }
+    int child_a(int n) const { return f.nodes[n - 1].first - 1; }
+
+    void emit(int n) {
+        const EuclNode& nd = f.nodes[n];
+        if (nd.op == EUCL_CSG_LEAF) {
+            out.push_back(MNode{M_PRIM, nd.prim, 0, (int)out.size()});
+            return;
+        }
+        if (nd.op == EUCL_CSG_UNION || nd.op == EUCL_CSG_INTERSECTION) {
+            // walk down the left spine while the right child is a leaf
+            std::vector<int> prims;
+            int m = n;
+            while (f.nodes[m].op == nd.op && f.nodes[child_b(m)].op == EUCL_CSG_LEAF) {
+                prims.push_back(f.nodes[child_b(m)].prim);
+                m = child_a(m);
+            }
+            if (f.nodes[m].op == EUCL_CSG_LEAF && !prims.empty()) {
+                prims.push_back(f.nodes[m].prim);
+                std::reverse(prims.begin(), prims.end());
+                bool consecutive = true;
+                for (size_t i = 1; i < prims.size(); ++i) consecutive = consecutive && prims[i] == prims[0] + (int)i;
+                if (consecutive) {
+                    const int count = (int)prims.size(), head = std::min(count, kMaxChain);
+                    const int first = (int)out.size();
+                    bool planes = true; // every leaf a hyperplane / half-space: enables the plane_chain fast path
+                    for (int i = 0; i < head; ++i) {
+                        const int k = f.prims[prims[(size_t)i]].kind;
+                        planes = planes && (k == EUCL_PRIM_HALFSPACE || k == EUCL_PRIM_HYPERPLANE);
+                    }
+                    out.push_back(MNode{M_CHAIN, prims[0], head | (planes ? 0x4000 : 0) | (nd.op << 16), first});
+                    for (int i = head; i < count; ++i) { // very long folds: the tail stays binary (same fold order)
+                        out.push_back(MNode{M_PRIM, prims[(size_t)i], 0, (int)out.size()});
+                        out.push_back(MNode{M_OP, nd.op, 0, first});
+                    }
+                    return;
+                }
+            }
+        }
+        const int first = (int)out.size();
+        emit(child_a(n));
+        emit(child_b(n));
+        out.push_back(MNode{M_OP, nd.op, 0, first});
+    }
+
+    // Worst-case arena use of the device evaluator (csg_first) for macro range [first, root]
+    bool fits(int first, int root, int* peak_out, int* depth_out) const {
+        std::vector<int> lens;
+        int top = 0, peak = 0, depth = 0;
+        for (int n = first; n <= root; ++n) {
+            const MNode& nd = out[(size_t)n];
+            if (nd.kind == M_PRIM) {
+                const int c = hits_of_prim(nd.a);
+                lens.push_back(c);
+                top += c;
+                peak = std::max(peak, top);
+            } else if (nd.kind == M_CHAIN) {
+                const int count = nd.b & 0x3fff;
+                peak = std::max(peak, top + 4 * count); // list + scratch, 2 * count each
+                int c = 0;
+                for (int i = 0; i < count; ++i) c += hits_of_prim(nd.a + i);
+                lens.push_back(c);
+                top += c;
+            } else {
+                const int bl = lens.back();
+                lens.pop_back();
+                const int al = lens.back();
+                lens.pop_back();
+                const int outn = al + bl + 2;
+                peak = std::max(peak, top + outn);
+                top = top - al - bl + outn;
+                lens.push_back(outn);
+            }
+            depth = std::max(depth, (int)lens.size());
+        }
+        *peak_out = peak;
+        *depth_out = depth;
+        return peak <= CSG_ARENA && depth <= CSG_LIST_STACK;
+    }
+};
 
 struct BlobWriter {
     std::vector<uint8_t> bytes;
@@ -277,8 +361,24 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     h.off_prim_v1 = w.put(v1.data(), v1.size());
     h.off_prim_s0 = w.put(s0.data(), s0.size());
     h.off_prim_s1 = w.put(s1.data(), s1.size());
-    h.off_nodes = w.put(flat->nodes, (size_t)flat->n_nodes);
-    h.off_entities = w.put(flat->entities, (size_t)flat->n_entities);
+    // macro CSG programs replace the binary node list on the device
+    MacroBuilder mb{*flat, {}};
+    std::vector<EuclEntity> dev_entities((size_t)flat->n_entities);
+    for (int e = 0; e < flat->n_entities; ++e) {
+        EuclEntity de = flat->entities[e];
+        de.node_first = (int)mb.out.size();
+        mb.emit(flat->entities[e].node_root);
+        de.node_root = (int)mb.out.size() - 1;
+        int peak = 0, depth = 0;
+        if (!mb.fits(de.node_first, de.node_root, &peak, &depth))
+            return bail(EUCL_ERR_SCENE_LIMIT, "entity " + std::to_string(e) + ": CSG program too large for the device evaluator (" +
+                                                  std::to_string(peak) + " arena slots of " + std::to_string(CSG_ARENA) + ", nesting " +
+                                                  std::to_string(depth) + ")");
+        dev_entities[(size_t)e] = de;
+    }
+    h.n_nodes = (int)mb.out.size();
+    h.off_nodes = w.put(mb.out.data(), mb.out.size());
+    h.off_entities = w.put(dev_entities.data(), dev_entities.size());
     h.off_materials = w.put(flat->materials, (size_t)flat->n_materials);
     h.off_transforms = w.put(flat->transforms, (size_t)flat->n_transforms);
     h.off_expr_ops = w.put(flat->expr_ops, (size_t)flat->n_expr_ops);

@@ -15,6 +15,7 @@ namespace eucl {
 
 constexpr int CSG_ARENA = 128;     // compact hits per thread (scene_create validates programs against it)
 constexpr int CSG_LIST_STACK = 16; // nesting depth of pending child lists
+constexpr int CHAIN_ROOT_CAP = 32; // hits of a chain that is an entity's whole shape (<= 16 leaves)
 
 struct CHit {
     double t;
@@ -105,25 +106,61 @@ __device__ __forceinline__ bool prim_inside(const SceneView& sv, int prim, const
     return kind == EUCL_PRIM_VOID; // hyperplane: never inside
 }
 
-// ComposableShape::is_point_inside (shape.rs:587-601) over the post-order range of node `n`,
-// with a bit stack instead of recursion (all operands are pure, so no short-circuit is needed).
+// ---------------------------------------------------------------------------------------------
+// Macro CSG programs.  The host (api_device.cu: build_macro_program) rewrites each entity's
+// post-order node list into macro nodes:
+//   M_PRIM  : one primitive
+//   M_CHAIN : a maximal left fold  ((l0 op l1) op l2) ... op l(n-1)  of n LEAF primitives with
+//             op = Intersection or Union and consecutive primitive indices (cuboid, hypercuboid,
+//             capped cylinder, wall sets ...), evaluated by one tight loop
+//   M_OP    : any other binary node, merging the lists of its two children
+// Evaluation order and every comparison are those of the nested binary iterators, so results are
+// identical; only the bookkeeping differs.
+enum : int { M_PRIM = 0, M_CHAIN = 1, M_OP = 2 };
+struct MNode {
+    int32_t kind;
+    int32_t a;     // PRIM: primitive; CHAIN: first primitive; OP: EuclCsgOp
+    int32_t b;     // CHAIN: count | 0x4000 if every leaf is a hyperplane / half-space | (EuclCsgOp << 16)
+    int32_t first; // first macro node of this subtree (post-order; children of OP n: b = n-1, a = mnodes[n-1].first-1)
+};
+
+// is_point_inside of a chain prefix: nested `&&` / `||` over pure operands = all / any
 template <int D>
-__device__ __forceinline__ bool node_inside(const SceneView& sv, int n, const Vec<D>& p) {
-    const int first = sv.nodes[n].first;
-    if (first == n) return prim_inside<D>(sv, sv.nodes[n].prim, p);
+__device__ __forceinline__ bool chain_inside(const SceneView& sv, int op, int p0, int count, const Vec<D>& p) {
+    for (int k = 0; k < count; ++k) {
+        const bool in = prim_inside<D>(sv, p0 + k, p);
+        if (op == EUCL_CSG_INTERSECTION) {
+            if (!in) return false;
+        } else if (in) {
+            return true;
+        }
+    }
+    return op == EUCL_CSG_INTERSECTION;
+}
+
+// ComposableShape::is_point_inside (shape.rs:587-601) of macro node `n`: a bit stack over the
+// macro post-order range (all operands are pure, so no short-circuit is needed between siblings).
+template <int D>
+__device__ __noinline__ bool node_inside(const SceneView& sv, int n, const Vec<D>& p) {
+    const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes);
+    const MNode root = mn[n];
+    if (root.kind == M_PRIM) return prim_inside<D>(sv, root.a, p);
+    if (root.kind == M_CHAIN) return chain_inside<D>(sv, root.b >> 16, root.a, root.b & 0x3fff, p);
     unsigned long long bits = 0ull;
     int sp = 0;
-    for (int m = first; m <= n; ++m) {
-        const EuclNode nd = sv.nodes[m];
-        if (nd.op == EUCL_CSG_LEAF) {
-            bits |= (unsigned long long)(prim_inside<D>(sv, nd.prim, p) ? 1 : 0) << sp;
+    for (int m = root.first; m <= n; ++m) {
+        const MNode nd = mn[m];
+        if (nd.kind != M_OP) {
+            const bool in = nd.kind == M_PRIM ? prim_inside<D>(sv, nd.a, p)
+                                              : chain_inside<D>(sv, nd.b >> 16, nd.a, nd.b & 0x3fff, p);
+            bits |= (unsigned long long)(in ? 1 : 0) << sp;
             ++sp;
         } else {
-            bool b = (bits >> (sp - 1)) & 1ull, a = (bits >> (sp - 2)) & 1ull;
-            bool r = nd.op == EUCL_CSG_UNION ? (a || b)
-                     : nd.op == EUCL_CSG_INTERSECTION ? (a && b)
-                     : nd.op == EUCL_CSG_COMPLEMENT ? (a && !b)
-                                                    : (a != b);
+            const bool b = (bits >> (sp - 1)) & 1ull, a = (bits >> (sp - 2)) & 1ull;
+            const bool r = nd.a == EUCL_CSG_UNION ? (a || b)
+                           : nd.a == EUCL_CSG_INTERSECTION ? (a && b)
+                           : nd.a == EUCL_CSG_COMPLEMENT ? (a && !b)
+                                                         : (a != b);
             sp -= 2;
             bits &= ~(3ull << sp);
             bits |= (unsigned long long)(r ? 1 : 0) << sp;
@@ -135,35 +172,211 @@ __device__ __forceinline__ bool node_inside(const SceneView& sv, int n, const Ve
 
 // Universe::material_at (mod.rs:229-251): first entity in list order containing the point
 template <int D>
-__device__ __forceinline__ int material_at(const SceneView& sv, const Vec<D>& p) {
+__device__ __noinline__ int material_at(const SceneView& sv, const Vec<D>& p) {
     for (int e = 0; e < sv.n_entities; ++e)
         if (node_inside<D>(sv, sv.entities[e].node_root, p)) return e;
     return -1;
 }
 
-// First item of the intersection stream of the CSG program [first, root]
+// Hit list of a chain macro node, "up to the first None", written to L (capacity cap; T is scratch
+// of the same size).  Step k merges the list so far (stream A) with the hits of leaf k (stream B)
+// exactly like IntersectionIterator / UnionIterator (shape.rs:212-340):
+//   both streams non-empty : take the closer one (ties and NaN -> b); a rejected hit is skipped
+//   one stream exhausted   : take from the other; a rejected hit ends the list (None)
+// A hit of A is tested against leaf k, a hit of B against the prefix l0..l(k-1).
+template <int D>
+__device__ __forceinline__ int chain_eval(const SceneView& sv, int op, int p0, int count, const Vec<D>& o, const Vec<D>& d,
+                                          CHit* L, CHit* T, int cap, bool first_only) {
+    double t0 = 0.0, t1 = 0.0;
+    int n = prim_roots<D>(sv, p0, o, d, t0, t1);
+    if (n > 0) L[0] = CHit{t0, p0, 0};
+    if (n > 1) L[1] = CHit{t1, p0, 1};
+    for (int k = 1; k < count; ++k) {
+        const int prim = p0 + k;
+        const int nb = prim_roots<D>(sv, prim, o, d, t0, t1);
+        const int limit = (first_only && k == count - 1) ? 1 : cap;
+        int ia = 0, ib = 0, m = 0;
+        while (m < limit) {
+            const bool has_a = ia < n, has_b = ib < nb;
+            if (!has_a && !has_b) break;
+            const double tb = ib == 0 ? t0 : t1;
+            CHit h;
+            bool in;
+            if (has_a && (!has_b || L[ia].t < tb)) {
+                h = L[ia++];
+                in = prim_inside<D>(sv, prim, o + d * h.t);
+            } else {
+                h = CHit{tb, prim, ib};
+                ++ib;
+                in = chain_inside<D>(sv, op, p0, k, o + d * h.t);
+            }
+            if (op == EUCL_CSG_INTERSECTION ? in : !in) T[m++] = h;
+            else if (!(has_a && has_b)) break;
+        }
+        for (int i = 0; i < m; ++i) L[i] = T[i];
+        n = m;
+    }
+    return n;
+}
+
+// Chain of exactly N plane-like leaves (half-spaces / hyperplanes: one hit each) -- cuboids (N = 6),
+// hypercuboids and 8-plane rooms (N = 8), wall sets (N = 4).  Same merge as chain_eval, but
+// organised for the GPU: all floating-point work (N roots, N hit points, N*(N-1) membership
+// tests, N*N distance comparisons) is straight-line and identical for every lane; the
+// data-dependent list bookkeeping then runs on integer bit masks only.  The list is a packed
+// array of 4-bit leaf indices.  Returns the list length; `t` receives the N root parameters.
+template <int D, int N>
+__device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, const Vec<D>& o, const Vec<D>& d,
+                                           bool first_only, double (&t)[N], unsigned long long& list_out) {
+    static_assert(N <= 8, "masks are packed N*N bits into 64");
+    const int np = sv.n_prims;
+    unsigned exists = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { // Hyperplane::intersect_linear, shape.rs:788-793
+        const Vec<D> nrm = load_vec<D>(sv.prim_v0 + p0 + i, np);
+        t[i] = -(dot(nrm, o) + sv.prim_s0[p0 + i]) / dot(nrm, d);
+        if (!(t[i] < 0.0)) exists |= 1u << i; // NaN and +inf pass
+    }
+    // inside[i] bit j: leaf j contains the hit point of leaf i (is_point_inside, shape.rs:812-817,873-881)
+    unsigned long long inside = 0ull, closer = 0ull;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const Vec<D> p = d * t[i] + o;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;
+            const int prim = p0 + j;
+            bool in = false;
+            if (sv.prim_kind[prim] == EUCL_PRIM_HALFSPACE) {
+                const double r = dot(load_vec<D>(sv.prim_v0 + prim, np), p) + sv.prim_s0[prim];
+                in = sv.prim_s1[prim] == rust_signum(r);
+            }
+            inside |= (unsigned long long)(in ? 1 : 0) << (i * N + j);
+            closer |= (unsigned long long)(t[i] < t[j] ? 1 : 0) << (i * N + j); // `a.distance < b.distance`
+        }
+    }
+    // integer replay of the N-1 merges (IntersectionIterator / UnionIterator, shape.rs:212-340)
+    const bool is_and = op == EUCL_CSG_INTERSECTION;
+    unsigned long long L = 0ull;
+    int n = exists & 1u;
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+        const unsigned prefix = (1u << k) - 1u;
+        const unsigned mask_k = (unsigned)(inside >> (k * N)) & prefix;
+        const bool b_in = is_and ? mask_k == prefix : mask_k != 0u; // inside the fold of leaves 0..k-1
+        bool b_pending = (exists >> k) & 1u;
+        const int limit = (first_only && k == N - 1) ? 1 : N;
+        unsigned long long T = 0ull;
+        int ia = 0, m = 0;
+        while (m < limit && (ia < n || b_pending)) {
+            const bool has_a = ia < n, both = has_a && b_pending;
+            const unsigned a = (unsigned)(L >> (4 * ia)) & 15u;
+            const bool take_a = has_a && (!b_pending || ((closer >> (a * N + k)) & 1ull));
+            bool in;
+            unsigned item;
+            if (take_a) {
+                item = a;
+                in = (inside >> (a * N + k)) & 1ull;
+                ++ia;
+            } else {
+                item = (unsigned)k;
+                in = b_in;
+                b_pending = false;
+            }
+            if (is_and ? in : !in) {
+                T |= (unsigned long long)item << (4 * m);
+                ++m;
+            } else if (!both) {
+                break; // None
+            }
+        }
+        L = T;
+        n = m;
+    }
+    list_out = L;
+    return n;
+}
+
+template <int N>
+__device__ __forceinline__ double select_t(const double (&t)[N], unsigned idx) {
+    double r = t[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) r = idx == (unsigned)i ? t[i] : r;
+    return r;
+}
+
+// Dispatch on the leaf count; returns false when N has no specialisation (generic chain_eval then).
+template <int D>
+__device__ __forceinline__ bool plane_chain_any(const SceneView& sv, int op, int p0, int count, const Vec<D>& o,
+                                                const Vec<D>& d, bool first_only, CHit* out, int& n_out) {
+    unsigned long long L = 0ull;
+    int n;
+    if (count == 2 * D) {
+        double t[2 * D];
+        n = plane_chain<D, 2 * D>(sv, op, p0, o, d, first_only, t, L);
+        for (int i = 0; i < n; ++i) {
+            const unsigned idx = (unsigned)(L >> (4 * i)) & 15u;
+            out[i] = CHit{select_t(t, idx), p0 + (int)idx, 0};
+        }
+    } else if (count == 4) {
+        double t[4];
+        n = plane_chain<D, 4>(sv, op, p0, o, d, first_only, t, L);
+        for (int i = 0; i < n; ++i) {
+            const unsigned idx = (unsigned)(L >> (4 * i)) & 15u;
+            out[i] = CHit{select_t(t, idx), p0 + (int)idx, 0};
+        }
+    } else {
+        return false;
+    }
+    n_out = n;
+    return true;
+}
+
+// A chain that is an entity's whole shape, generic leaves: only the first item is needed.
+template <int D>
+__device__ __noinline__ bool chain_first_generic(const SceneView& sv, int op, int p0, int count, const Vec<D>& o,
+                                                 const Vec<D>& d, CHit& out) {
+    CHit lists[2][CHAIN_ROOT_CAP];
+    const int c = chain_eval<D>(sv, op, p0, count, o, d, lists[0], lists[1], CHAIN_ROOT_CAP, true);
+    out = lists[0][0];
+    return c > 0;
+}
+
+// First item of the intersection stream of the macro program [first, root]
 // (ComposableShape::intersect_linear + the four merge iterators, shape.rs:204-584).
 template <int D>
-__device__ bool csg_first(const SceneView& sv, int first, int root, const Vec<D>& o, const Vec<D>& d, CHit& out) {
+__device__ __noinline__ bool csg_first(const SceneView& sv, int first, int root, const Vec<D>& o, const Vec<D>& d, CHit& out) {
+    const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes);
     CHit arena[CSG_ARENA];
     int lstart[CSG_LIST_STACK], llen[CSG_LIST_STACK];
     int sp = 0, top = 0;
     for (int n = first; n <= root; ++n) {
-        const EuclNode nd = sv.nodes[n];
-        if (nd.op == EUCL_CSG_LEAF) {
+        const MNode nd = mn[n];
+        if (nd.kind == M_PRIM) {
             double t0 = 0.0, t1 = 0.0;
-            int c = prim_roots<D>(sv, nd.prim, o, d, t0, t1);
+            const int c = prim_roots<D>(sv, nd.a, o, d, t0, t1);
             lstart[sp] = top;
             llen[sp] = c;
             ++sp;
-            if (c > 0) arena[top++] = CHit{t0, nd.prim, 0};
-            if (c > 1) arena[top++] = CHit{t1, nd.prim, 1};
+            if (c > 0) arena[top++] = CHit{t0, nd.a, 0};
+            if (c > 1) arena[top++] = CHit{t1, nd.a, 1};
+            continue;
+        }
+        if (nd.kind == M_CHAIN) {
+            const int count = nd.b & 0x3fff, cap = 2 * count;
+            int c = 0;
+            if (!((nd.b & 0x4000) && plane_chain_any<D>(sv, nd.b >> 16, nd.a, count, o, d, n == root, arena + top, c)))
+                c = chain_eval<D>(sv, nd.b >> 16, nd.a, count, o, d, arena + top, arena + top + cap, cap, n == root);
+            lstart[sp] = top;
+            llen[sp] = c;
+            ++sp;
+            top += c;
             continue;
         }
         const int b0 = lstart[sp - 1], bl = llen[sp - 1], a0 = lstart[sp - 2], al = llen[sp - 2];
         sp -= 2;
-        const int nb = n - 1, na = sv.nodes[n - 1].first - 1;
-        const int op = nd.op;
+        const int nb = n - 1, na = mn[n - 1].first - 1;
+        const int op = nd.a;
         const int out0 = top;
         // The entity root only ever yields its first item (mod.rs:110-112); inner nodes are
         // bounded because a Complement with an exhausted `b` repeats `a` forever (shape.rs:392).
@@ -263,11 +476,21 @@ __device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec
         if (ent.surface < 0) continue;
         CHit h;
         bool found;
-        if (ent.node_first == ent.node_root) {
+        const MNode root = reinterpret_cast<const MNode*>(sv.nodes)[ent.node_root];
+        if (root.kind == M_PRIM) {
             double t0 = 0.0, t1 = 0.0;
-            const int prim = sv.nodes[ent.node_root].prim;
-            found = prim_roots<D>(sv, prim, o, d, t0, t1) > 0;
-            h = CHit{t0, prim, 0};
+            found = prim_roots<D>(sv, root.a, o, d, t0, t1) > 0;
+            h = CHit{t0, root.a, 0};
+        } else if (root.kind == M_CHAIN) {
+            const int count = root.b & 0x3fff;
+            CHit first_hit[2 * D];
+            int c = 0;
+            if ((root.b & 0x4000) && plane_chain_any<D>(sv, root.b >> 16, root.a, count, o, d, true, first_hit, c)) {
+                found = c > 0;
+                h = first_hit[0];
+            } else {
+                found = chain_first_generic<D>(sv, root.b >> 16, root.a, count, o, d, h);
+            }
         } else {
             found = csg_first<D>(sv, ent.node_first, ent.node_root, o, d, h);
         }

@@ -85,7 +85,7 @@ __device__ __forceinline__ double blend_channel(int fn, double a, double b, doub
 }
 
 // palette Blend on premultiplied colours: `s` = self (source), `d` = argument (destination)
-__device__ __forceinline__ Pre blend_pre(int fn, const Pre& s, const Pre& d) {
+__device__ __noinline__ Pre blend_pre(int fn, const Pre& s, const Pre& d) {
     const double sa = s.a, da = d.a;
     double alpha;
     switch (fn) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ Rgba hue_to_rgba(double hue_degrees) {
 }
 
 // noise 0.4.1 Perlin::get([f64; 4]) with the seed-0 permutation table staged in shared memory
-__device__ __forceinline__ double perlin4(const uint8_t* perm, const double point[4]) {
+__device__ __noinline__ double perlin4(const uint8_t* perm, const double point[4]) {
     const double diag = 0.577350269189625764077083524672081875;
     double near_d[4], far_d[4];
     long long near_c[4];
@@ -146,7 +146,7 @@ __device__ __forceinline__ double perlin4(const uint8_t* perm, const double poin
         far_d[k] = near_d[k] - 1.0;
     }
     double total = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int corner = 0; corner < 16; ++corner) {
         double dd[4];
         unsigned cc[4];
@@ -216,15 +216,15 @@ __device__ __forceinline__ Rgba fetch_texel(cudaTextureObject_t tex, const EuclT
 
 // MappedTextureImpl::get_color with uv_sphere (+ uv_derank in 4-D) and the two image filters
 template <int D>
-__device__ __forceinline__ Rgba mapped_color(const SceneView& sv, int mapped, const Vec<D>& point) {
+__device__ __noinline__ Rgba mapped_color(const SceneView& sv, int mapped, const Vec<D>& point) {
     if (mapped < 0) return Rgba{0.0, 0.0, 0.0, 0.0}; // MappedTextureTransparent
     const EuclMappedTexture mt = sv.mapped[mapped];
     Vec<3> p;
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
     p = normalize(p);
-    const double u = 0.5 + eucl_det::det_atan2(p[1], p[0]) / (2.0 * kPi);
-    const double v = 0.5 - eucl_det::det_asin(p[2]) / kPi;
+    const double u = 0.5 + dm_atan2(p[1], p[0]) / (2.0 * kPi);
+    const double v = 0.5 - dm_asin(p[2]) / kPi;
     const EuclTexture t = sv.textures[mt.texture];
     const cudaTextureObject_t tex = sv.tex_objects[mt.texture];
     const double width = (double)t.width, height = (double)t.height;
@@ -254,7 +254,7 @@ __device__ __forceinline__ Rgba mapped_color(const SceneView& sv, int mapped, co
 // --- materials ---------------------------------------------------------------------------------
 
 // meval-style RPN program (compiled on the host from the scene's expression strings)
-__device__ inline double eval_expr(const SceneView& sv, int first, int len, const double* vars) {
+__device__ __noinline__ double eval_expr(const SceneView& sv, int first, int len, const double* vars) {
     double st[16];
     int sp = 0;
     for (int i = first; i < first + len; ++i) {
@@ -272,12 +272,12 @@ __device__ inline double eval_expr(const SceneView& sv, int first, int len, cons
             case EUCL_FN_ABS: r = fabs(x); break;
             case EUCL_FN_EXP: r = exp(x); break;
             case EUCL_FN_LN: r = log(x); break;
-            case EUCL_FN_SIN: r = eucl_det::det_sin(x); break;
-            case EUCL_FN_COS: r = eucl_det::det_cos(x); break;
+            case EUCL_FN_SIN: r = dm_sin(x); break;
+            case EUCL_FN_COS: r = dm_cos(x); break;
             case EUCL_FN_TAN: r = tan(x); break;
-            case EUCL_FN_ASIN: r = eucl_det::det_asin(x); break;
-            case EUCL_FN_ACOS: r = eucl_det::det_acos(x); break;
-            case EUCL_FN_ATAN: r = eucl_det::det_atan(x); break;
+            case EUCL_FN_ASIN: r = dm_asin(x); break;
+            case EUCL_FN_ACOS: r = dm_acos(x); break;
+            case EUCL_FN_ATAN: r = dm_atan(x); break;
             case EUCL_FN_SINH: r = sinh(x); break;
             case EUCL_FN_COSH: r = cosh(x); break;
             case EUCL_FN_TANH: r = tanh(x); break;
@@ -297,7 +297,7 @@ __device__ inline double eval_expr(const SceneView& sv, int first, int len, cons
             case EUCL_EX_REM: r = fmod(a, b); break;
             case EUCL_EX_POW: r = pow(a, b); break;
             case EUCL_EX_FUNC2:
-                if (o.arg == EUCL_FN_ATAN2) r = eucl_det::det_atan2(a, b);
+                if (o.arg == EUCL_FN_ATAN2) r = dm_atan2(a, b);
                 else if (o.arg == EUCL_FN_MAX) r = fmax(a, b);
                 else r = fmin(a, b);
                 break;
@@ -311,7 +311,7 @@ __device__ inline double eval_expr(const SceneView& sv, int first, int len, cons
 // ComponentTransformation::transform_with (material.rs:91-112): all component expressions see the
 // same input vector
 template <int D>
-__device__ inline void apply_transform(const SceneView& sv, const EuclTransform& t, bool inverse, Vec<D>& v) {
+__device__ __noinline__ void apply_transform(const SceneView& sv, const EuclTransform& t, bool inverse, Vec<D>& v) {
     double in[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) in[k] = v[k];
@@ -343,7 +343,7 @@ struct HitContext { // the fields of TracingContext (shape.rs:111-123) the provi
 
 // util.rs:631-666: rotate `v` in the plane spanned by (self_, other) by `angle`
 template <int D>
-__device__ inline Vec<D> general_rotation(const Vec<D>& self_, const Vec<D>& other, double angle, const Vec<D>& v) {
+__device__ __noinline__ Vec<D> general_rotation(const Vec<D>& self_, const Vec<D>& other, double angle, const Vec<D>& v) {
     double original[D][D], result[D][D]; // [row][col]
 #pragma unroll
     for (int r = 0; r < D; ++r)
@@ -384,7 +384,7 @@ __device__ inline Vec<D> general_rotation(const Vec<D>& self_, const Vec<D>& oth
     for (int r = 0; r < D; ++r)
 #pragma unroll
         for (int c = 0; c < D; ++c) rot[r][c] = r == c ? 1.0 : 0.0;
-    const double ca = eucl_det::det_cos(angle), sa = eucl_det::det_sin(angle);
+    const double ca = dm_cos(angle), sa = dm_sin(angle);
     rot[0][0] = ca;
     rot[0][1] = -sa;
     rot[1][0] = sa;
@@ -430,9 +430,9 @@ __device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, const 
     const double from_theta = angle_between(dir, normal);
     const double from_index = exiting ? sf.ratio_a : sf.ratio_b;
     const double to_index = exiting ? sf.ratio_b : sf.ratio_a;
-    const double to_theta = eucl_det::det_asin((from_index / to_index) * eucl_det::det_sin(from_theta));
+    const double to_theta = dm_asin((from_index / to_index) * dm_sin(from_theta));
     if (isnan(to_theta)) return 1.0;
-    const double cf = eucl_det::det_cos(from_theta), ct = eucl_det::det_cos(to_theta);
+    const double cf = dm_cos(from_theta), ct = dm_cos(to_theta);
     const double p1s = from_index * cf, p2s = to_index * ct;
     const double p1p = from_index * ct, p2p = to_index * cf;
     const double rs = (p1s - p2s) / (p1s + p2s);
@@ -454,14 +454,14 @@ __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, con
     const Vec<D> normal = -normal_closer;
     const double from_theta = angle_between(dir, normal);
     const double modifier = exiting ? sf.thr_a : 1.0 / sf.thr_a;
-    const double to_theta = eucl_det::det_asin(modifier * eucl_det::det_sin(from_theta));
+    const double to_theta = dm_asin(modifier * dm_sin(from_theta));
     const double angle_delta = to_theta - from_theta;
     return general_rotation<D>(normal, dir, angle_delta, dir);
 }
 
 // The surface colour program (postfix) of surface `sf` at a hit.
 template <int D>
-__device__ inline Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& location,
+__device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& location,
                                      const Vec<D>& normal_raw, const Vec<D>& normal_closer, double time_millis) {
     Rgba stack[8];
     int sp = 0;

@@ -66,13 +66,23 @@ __device__ __forceinline__ double norm(const Vec<D>& a) { return sqrt(norm_squar
 template <int D>
 __device__ __forceinline__ Vec<D> normalize(const Vec<D>& a) { return a / norm(a); }
 
+// Out-of-line copies of the deterministic libm (include/eucl_detmath.h): these bodies are 40-100
+// instructions each and are called from many places; inlining them everywhere made the shade kernel
+// 0.5 MB of SASS and instruction-fetch bound (profiles/r1_ncu_k_shade_baseline.txt: stall_no_instruction).
+static __device__ __noinline__ double dm_acos(double x) { return eucl_det::det_acos(x); }
+static __device__ __noinline__ double dm_asin(double x) { return eucl_det::det_asin(x); }
+static __device__ __noinline__ double dm_sin(double x) { return eucl_det::det_sin(x); }
+static __device__ __noinline__ double dm_cos(double x) { return eucl_det::det_cos(x); }
+static __device__ __noinline__ double dm_atan(double x) { return eucl_det::det_atan(x); }
+static __device__ __noinline__ double dm_atan2(double y, double x) { return eucl_det::det_atan2(y, x); }
+
 // util.rs:712-722: acos of the normalised dot product, NaN -> 0
 template <int D>
 __device__ __forceinline__ double angle_cos(const Vec<D>& a, const Vec<D>& b) {
     return dot(a, b) / (norm(a) * norm(b));
 }
 __device__ __forceinline__ double angle_from_cos(double c) {
-    double r = eucl_det::det_acos(c); // deterministic libm shared with the oracle (include/eucl_detmath.h)
+    double r = dm_acos(c); // deterministic libm shared with the oracle (include/eucl_detmath.h)
     return isnan(r) ? 0.0 : r;
 }
 template <int D>
