@@ -14,8 +14,9 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-BUILD = ROOT / "build"
-LIB = PKG / "libeuclider_b200.so"
+BUILD = ROOT / ("build" + os.environ.get("EUCL_LIB_SUFFIX", ""))
+SUFFIX = os.environ.get("EUCL_LIB_SUFFIX", "")  # experiment builds: EUCL_LIB_SUFFIX=_x EUCL_NVCC_EXTRA="-D..."
+LIB = PKG / f"libeuclider_b200{SUFFIX}.so"
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
@@ -25,6 +26,7 @@ GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
               "-Xcompiler", "-fPIC,-Wall,-ffp-contract=off", "-Xptxas", "-v"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off"]
+NVCC_FLAGS += os.environ.get("EUCL_NVCC_EXTRA", "").split()
 
 
 def _sources():

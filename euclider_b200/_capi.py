@@ -144,7 +144,9 @@ PROTOTYPES = {
     "eucl_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
-LIB_PATH = Path(__file__).resolve().parent / "libeuclider_b200.so"
+import os as _os
+
+LIB_PATH = Path(__file__).resolve().parent / f"libeuclider_b200{_os.environ.get('EUCL_LIB_SUFFIX', '')}.so"
 _lib = None
 
 

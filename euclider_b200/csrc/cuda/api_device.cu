@@ -73,6 +73,8 @@ struct EuclScene {
     DeviceBuffer small;    // counters
     DeviceBuffer frame;    // device frame buffer for eucl_render (host output)
     DeviceBuffer hit_ids;  // device hit-id map for eucl_render
+    DeviceBuffer order;    // per-bin node lists of the level being shaded
+    int n_entities = 0;
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
     int32_t* h_small = nullptr; // pinned mirror of the counters
@@ -80,7 +82,7 @@ struct EuclScene {
 
 namespace {
 
-constexpr int kSmallInts = 4 * (EUCL_MAX_LEVELS + 1) + 16; // per chunk: count, level_off, flags
+constexpr int kSmallInts = 4 * (EUCL_MAX_LEVELS + 1) + 16 + (EUCL_MAX_LEVELS + 1) * kMaxBins; // count, level_off, flags, bins
 struct SmallLayout {                                        // one per chunk, in ints
     static constexpr int count = 0;
     static constexpr int level_off = EUCL_MAX_LEVELS + 1;
@@ -88,7 +90,8 @@ struct SmallLayout {                                        // one per chunk, in
     static constexpr int cam_entity = overflow + 1;
     static constexpr int undefined64 = overflow + 2;                  // 8-byte aligned (even index)
     static constexpr int mega64 = undefined64 + 2;                    // (EUCL_MAX_LEVELS + 1) x u64
-    static constexpr int total = mega64 + 2 * (EUCL_MAX_LEVELS + 1);
+    static constexpr int bins = mega64 + 2 * (EUCL_MAX_LEVELS + 1);       // [level][kMaxBins]
+    static constexpr int total = bins + (EUCL_MAX_LEVELS + 1) * kMaxBins;
 };
 static_assert(SmallLayout::undefined64 % 2 == 0, "u64 counters must be 8-byte aligned");
 static_assert(SmallLayout::total <= kSmallInts, "small buffer layout");
@@ -165,10 +168,10 @@ struct MacroBuilder {
                 if (consecutive) {
                     const int count = (int)prims.size(), head = std::min(count, kMaxChain);
                     const int first = (int)out.size();
-                    bool planes = true; // every leaf a hyperplane / half-space: enables the plane_chain fast path
+                    bool planes = true; // every leaf a half-space with signum +-1: enables the plane_chain fast path
                     for (int i = 0; i < head; ++i) {
-                        const int k = f.prims[prims[(size_t)i]].kind;
-                        planes = planes && (k == EUCL_PRIM_HALFSPACE || k == EUCL_PRIM_HYPERPLANE);
+                        const EuclPrim& pr = f.prims[prims[(size_t)i]];
+                        planes = planes && pr.kind == EUCL_PRIM_HALFSPACE && (pr.s1 == 1.0 || pr.s1 == -1.0);
                     }
                     out.push_back(MNode{M_CHAIN, prims[0], head | (planes ? 0x4000 : 0) | (nd.op << 16), first});
                     for (int i = head; i < count; ++i) { // very long folds: the tail stays binary (same fold order)
@@ -260,6 +263,7 @@ void eucl_scene_destroy(EuclScene* s) {
     s->small.release();
     s->frame.release();
     s->hit_ids.release();
+    s->order.release();
     if (s->h_small) cudaFreeHost(s->h_small);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -286,6 +290,7 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     EuclScene* s = new EuclScene();
     s->device = device;
     s->dim = flat->dim;
+    s->n_entities = flat->n_entities;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     auto bail = [&](int st, const std::string& msg) {
         eucl_scene_destroy(s);
@@ -480,6 +485,10 @@ Workspace carve(EuclScene* s, int dim, int cap) {
     ws.cam_entity = small + SmallLayout::cam_entity;
     ws.undefined_count = (unsigned long long*)(small + SmallLayout::undefined64);
     ws.mega_level_counts = (unsigned long long*)(small + SmallLayout::mega64);
+    ws.bin_count = small + SmallLayout::bins;
+    ws.order = (int32_t*)s->order.ptr;
+    const bool bin = s->order.ptr != nullptr;
+    ws.n_bins = bin ? s->n_entities + 1 : 1;
     return ws;
 }
 
@@ -522,6 +531,9 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     EUCL_CUDA(cudaStreamSynchronize(s->stream));
                     EUCL_CUDA(s->nodes.ensure(arena_bytes(dim, (size_t)want)));
                     s->arena_capacity = (int)want;
+                    // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
+                    if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1))
+                        EUCL_CUDA(s->order.ensure(sizeof(int32_t) * (size_t)(s->n_entities + 1) * (size_t)want));
                 }
                 Workspace ws = carve(s, dim, s->arena_capacity);
                 EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));

@@ -120,7 +120,7 @@ enum : int { M_PRIM = 0, M_CHAIN = 1, M_OP = 2 };
 struct MNode {
     int32_t kind;
     int32_t a;     // PRIM: primitive; CHAIN: first primitive; OP: EuclCsgOp
-    int32_t b;     // CHAIN: count | 0x4000 if every leaf is a hyperplane / half-space | (EuclCsgOp << 16)
+    int32_t b;     // CHAIN: count | 0x4000 if every leaf is a half-space with signum +-1 | (EuclCsgOp << 16)
     int32_t first; // first macro node of this subtree (post-order; children of OP n: b = n-1, a = mnodes[n-1].first-1)
 };
 
@@ -229,28 +229,30 @@ template <int D, int N>
 __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, const Vec<D>& o, const Vec<D>& d,
                                            bool first_only, double (&t)[N], unsigned long long& list_out) {
     static_assert(N <= 8, "masks are packed N*N bits into 64");
+    // The host only routes chains here whose leaves are ALL half-spaces with signum = +-1.
     const int np = sv.n_prims;
     unsigned exists = 0u;
+    Vec<D> pt[N]; // hit points, kept in registers so every plane is loaded once below
 #pragma unroll
     for (int i = 0; i < N; ++i) { // Hyperplane::intersect_linear, shape.rs:788-793
         const Vec<D> nrm = load_vec<D>(sv.prim_v0 + p0 + i, np);
         t[i] = -(dot(nrm, o) + sv.prim_s0[p0 + i]) / dot(nrm, d);
         if (!(t[i] < 0.0)) exists |= 1u << i; // NaN and +inf pass
+        pt[i] = d * t[i] + o;
     }
-    // inside[i] bit j: leaf j contains the hit point of leaf i (is_point_inside, shape.rs:812-817,873-881)
+    // inside[i] bit j: half-space j contains the hit point of leaf i (shape.rs:873-881):
+    // signum == (n.p + c).signum(), Rust signum = +-1 by sign bit, NaN for NaN
     unsigned long long inside = 0ull, closer = 0ull;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const Vec<D> p = d * t[i] + o;
+    for (int j = 0; j < N; ++j) {
+        const Vec<D> nrm = load_vec<D>(sv.prim_v0 + p0 + j, np);
+        const double c = sv.prim_s0[p0 + j];
+        const bool s_neg = sv.prim_s1[p0 + j] < 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
+        for (int i = 0; i < N; ++i) {
             if (j == i) continue;
-            const int prim = p0 + j;
-            bool in = false;
-            if (sv.prim_kind[prim] == EUCL_PRIM_HALFSPACE) {
-                const double r = dot(load_vec<D>(sv.prim_v0 + prim, np), p) + sv.prim_s0[prim];
-                in = sv.prim_s1[prim] == rust_signum(r);
-            }
+            const double r = dot(nrm, pt[i]) + c;
+            const bool in = !isnan(r) && ((__double2hiint(r) < 0) == s_neg);
             inside |= (unsigned long long)(in ? 1 : 0) << (i * N + j);
             closer |= (unsigned long long)(t[i] < t[j] ? 1 : 0) << (i * N + j); // `a.distance < b.distance`
         }

@@ -16,6 +16,15 @@ namespace {
 
 extern __shared__ __align__(16) unsigned char g_smem[];
 
+// resident CTAs per SM the register allocator must allow (occupancy hides the long FP64
+// div/sqrt dependency chains and the instruction-fetch bubbles of this branchy code)
+#ifndef EUCL_INTERSECT_MIN_BLOCKS
+#define EUCL_INTERSECT_MIN_BLOCKS 4
+#endif
+#ifndef EUCL_SHADE_MIN_BLOCKS
+#define EUCL_SHADE_MIN_BLOCKS 3
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // node arena access (planes of double2 -> 128-bit coalesced transactions)
 
@@ -241,28 +250,48 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
 
 // K2: closest hit of every ray of one level.
 template <int D>
-__global__ void __launch_bounds__(kBlock) k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level) {
+__global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level) {
     if (*ws.overflow) return; // an earlier level did not fit: the host grows the arena and retries
     const int off = ws.level_off[level], cnt = ws.count[level];
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.level_off[level + 1] = off + cnt;
     if (blockIdx.x * blockDim.x >= cnt) return;
     const SceneView& sv = stage_scene(blob, g_smem);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cnt; base += stride) {
+        const int i = base + (int)lane;
         const int node = off + i;
-        if (ws.ray_cur[node] < 0) continue;
-        Vec<D> o, d, p, n;
-        load_ray<D>(ws, node, o, d);
-        bool exiting = false;
-        const int ent = intersect_ray<D>(sv, o, d, exiting, p, n);
-        ws.hit_ei[node] = make_int2(ent, exiting ? 1 : 0);
-        if (ent >= 0) store_hit<D>(ws, node, p, n);
+        const bool valid = i < cnt && ws.ray_cur[node] >= 0;
+        int ent = -1;
+        if (valid) {
+            Vec<D> o, d, p, n;
+            load_ray<D>(ws, node, o, d);
+            bool exiting = false;
+            ent = intersect_ray<D>(sv, o, d, exiting, p, n);
+            ws.hit_ei[node] = make_int2(ent, exiting ? 1 : 0);
+            if (ent >= 0) store_hit<D>(ws, node, p, n);
+        }
+        if (ws.n_bins > 1) {
+            // group the level's nodes by hit entity so that a shading warp runs ONE surface program:
+            // one atomicAdd per (warp, distinct key), ranks from the match mask
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const int key = ent + 1;
+                const unsigned peers = __match_any_sync(active, key);
+                const int leader = __ffs(peers) - 1;
+                int slot = 0;
+                if ((int)lane == leader) slot = atomicAdd(&ws.bin_count[level * kMaxBins + key], __popc(peers));
+                slot = __shfl_sync(peers, slot, leader);
+                ws.order[(size_t)key * ws.capacity + slot + __popc(peers & ((1u << lane) - 1u))] = node;
+            }
+        }
     }
 }
 
 // K3: shade every node of one level and append its children to the next level.  Children are
 // appended with one atomicAdd per warp (ballot + popc ranks).
 template <int D>
-__global__ void __launch_bounds__(kBlock) k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
+__global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
                                                   Workspace ws, int level, int32_t* __restrict__ hit_ids_out) {
     const int off = ws.level_off[level], cnt = ws.count[level];
     if (blockIdx.x * blockDim.x >= cnt) return;
@@ -272,10 +301,31 @@ __global__ void __launch_bounds__(kBlock) k_shade(const uint8_t* __restrict__ bl
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cnt; base += stride) {
-        const int i = base + (int)lane;
-        const int node = off + i;
-        const bool valid = i < cnt && ws.ray_cur[node] >= 0;
+    // binned levels: position g of the concatenated bins -> (bin, index) through the bin prefix sums
+    __shared__ int s_prefix[kMaxBins + 1];
+    const bool binned = ws.n_bins > 1 && !last_level;
+    if (binned && threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < ws.n_bins; ++b) {
+            s_prefix[b] = acc;
+            acc += ws.bin_count[level * kMaxBins + b];
+        }
+        s_prefix[ws.n_bins] = acc;
+    }
+    __syncthreads();
+    const int total = binned ? s_prefix[ws.n_bins] : cnt;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
+        const int g = base + (int)lane;
+        int node = off + g;
+        bool valid = g < total;
+        if (binned && valid) {
+            int b = 0;
+            while (g >= s_prefix[b + 1]) ++b;
+            node = ws.order[(size_t)b * ws.capacity + (g - s_prefix[b])];
+        } else if (valid) {
+            valid = ws.ray_cur[node] >= 0;
+        }
+        const int i = node - off;
         ShadeOut<D> so;
         so.t_emit = false;
         so.r_emit = false;

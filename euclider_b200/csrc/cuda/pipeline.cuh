@@ -72,6 +72,10 @@ struct Workspace {
     int32_t* level_off; // [EUCL_MAX_LEVELS + 1] first node id of each level
     int32_t* overflow;  // set when a child could not be appended
     int32_t* cam_entity; // material_at(camera location), -1 if none
+    int32_t n_bins;      // 1: shade in node order; else n_entities + 1 bins keyed by hit entity (0 = miss)
+    int32_t _pad2;
+    int32_t* bin_count;  // [EUCL_MAX_LEVELS + 1][kMaxBins] nodes per (level, hit-entity bin)
+    int32_t* order;      // [n_bins][capacity] node ids of the current level grouped by bin (reused per level)
     unsigned long long* undefined_count;   // nodes that touched a corner the reference leaves undefined
     unsigned long long* mega_level_counts; // [EUCL_MAX_LEVELS + 1] nodes per level, megakernel pipeline only
 };
@@ -84,6 +88,7 @@ struct Launch {
 };
 
 constexpr int kBlock = 128;
+constexpr int kMaxBins = 32; // shade-coherence bins (hit entity + 1); scenes with more entities shade unbinned
 
 // kernels.cu
 void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws);
