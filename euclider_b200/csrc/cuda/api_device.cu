@@ -366,6 +366,13 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     h.off_prim_v1 = w.put(v1.data(), v1.size());
     h.off_prim_s0 = w.put(s0.data(), s0.size());
     h.off_prim_s1 = w.put(s1.data(), s1.size());
+    std::vector<double> planes((size_t)np * kPlaneStride, 0.0); // AoS copy: [v0[0..3], s0, s1] per primitive
+    for (int i = 0; i < flat->n_prims; ++i) {
+        for (int k = 0; k < EUCL_MAX_DIM; ++k) planes[(size_t)i * kPlaneStride + k] = flat->prims[i].v0[k];
+        planes[(size_t)i * kPlaneStride + 4] = flat->prims[i].s0;
+        planes[(size_t)i * kPlaneStride + 5] = flat->prims[i].s1;
+    }
+    h.off_planes = w.put(planes.data(), planes.size());
     // macro CSG programs replace the binary node list on the device
     MacroBuilder mb{*flat, {}};
     std::vector<EuclEntity> dev_entities((size_t)flat->n_entities);
@@ -400,7 +407,8 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     h.blob_bytes = (int)w.bytes.size();
     std::memcpy(w.bytes.data(), &h, sizeof h);
     s->blob_bytes = h.blob_bytes;
-    s->smem_bytes = scene_smem_bytes(h.blob_bytes);
+    // staged scene + the per-thread plane_chain scratch columns (kernels.cu: plane_scratch)
+    s->smem_bytes = scene_smem_bytes(h.blob_bytes) + sizeof(double) * kPlaneChainMax * kBlock;
     int smem_optin = 0;
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (s->smem_bytes > (size_t)smem_optin)

@@ -51,10 +51,10 @@ template <int D>
 __device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const Vec<D>& o, const Vec<D>& d, double& t0,
                                           double& t1) {
     const int n = sv.n_prims;
-    const int kind = sv.prim_kind[prim];
+    const int kind = sv.prim_kind()[prim];
     if (kind == EUCL_PRIM_SPHERE) { // shape.rs:662-670
-        Vec<D> center = load_vec<D>(sv.prim_v0 + prim, n);
-        double radius = sv.prim_s0[prim];
+        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
+        double radius = sv.prim_s0()[prim];
         Vec<D> rel = o - center;
         double a = norm_squared(d);
         double b = 2.0 * dot(d, rel);
@@ -62,16 +62,16 @@ __device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const V
         return quadratic_hits(a, b, c, t0, t1);
     }
     if (kind == EUCL_PRIM_HYPERPLANE || kind == EUCL_PRIM_HALFSPACE) { // shape.rs:788-793
-        Vec<D> nrm = load_vec<D>(sv.prim_v0 + prim, n);
-        double t = -(dot(nrm, o) + sv.prim_s0[prim]) / dot(nrm, d);
+        Vec<D> nrm = load_vec<D>(sv.prim_v0() + prim, n);
+        double t = -(dot(nrm, o) + sv.prim_s0()[prim]) / dot(nrm, d);
         if (t < 0.0) return 0; // NaN and +inf pass, exactly like the reference
         t0 = t;
         return 1;
     }
     if (kind == EUCL_PRIM_CYLINDER) { // shape.rs:946-953
-        Vec<D> center = load_vec<D>(sv.prim_v0 + prim, n);
-        Vec<D> axis = load_vec<D>(sv.prim_v1 + prim, n);
-        double radius = sv.prim_s0[prim];
+        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
+        Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
+        double radius = sv.prim_s0()[prim];
         Vec<D> a_vec = d - axis * dot(d, axis);
         Vec<D> delta = o - center;
         Vec<D> c_vec = delta - axis * dot(delta, axis);
@@ -87,19 +87,19 @@ __device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const V
 template <int D>
 __device__ __forceinline__ bool prim_inside(const SceneView& sv, int prim, const Vec<D>& p) {
     const int n = sv.n_prims;
-    const int kind = sv.prim_kind[prim];
+    const int kind = sv.prim_kind()[prim];
     if (kind == EUCL_PRIM_HALFSPACE) {
-        double r = dot(load_vec<D>(sv.prim_v0 + prim, n), p) + sv.prim_s0[prim];
-        return sv.prim_s1[prim] == rust_signum(r);
+        double r = dot(load_vec<D>(sv.prim_v0() + prim, n), p) + sv.prim_s0()[prim];
+        return sv.prim_s1()[prim] == rust_signum(r);
     }
     if (kind == EUCL_PRIM_SPHERE) {
-        double radius = sv.prim_s0[prim];
-        return norm_squared(load_vec<D>(sv.prim_v0 + prim, n) - p) <= radius * radius;
+        double radius = sv.prim_s0()[prim];
+        return norm_squared(load_vec<D>(sv.prim_v0() + prim, n) - p) <= radius * radius;
     }
     if (kind == EUCL_PRIM_CYLINDER) {
-        Vec<D> center = load_vec<D>(sv.prim_v0 + prim, n);
-        Vec<D> axis = load_vec<D>(sv.prim_v1 + prim, n);
-        double radius = sv.prim_s0[prim];
+        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
+        Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
+        double radius = sv.prim_s0()[prim];
         Vec<D> on_axis = axis * dot(axis, p - center) + center;
         return norm_squared(p - on_axis) <= radius * radius;
     }
@@ -142,7 +142,7 @@ __device__ __forceinline__ bool chain_inside(const SceneView& sv, int op, int p0
 // macro post-order range (all operands are pure, so no short-circuit is needed between siblings).
 template <int D>
 __device__ __noinline__ bool node_inside(const SceneView& sv, int n, const Vec<D>& p) {
-    const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes);
+    const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes());
     const MNode root = mn[n];
     if (root.kind == M_PRIM) return prim_inside<D>(sv, root.a, p);
     if (root.kind == M_CHAIN) return chain_inside<D>(sv, root.b >> 16, root.a, root.b & 0x3fff, p);
@@ -174,7 +174,7 @@ __device__ __noinline__ bool node_inside(const SceneView& sv, int n, const Vec<D
 template <int D>
 __device__ __noinline__ int material_at(const SceneView& sv, const Vec<D>& p) {
     for (int e = 0; e < sv.n_entities; ++e)
-        if (node_inside<D>(sv, sv.entities[e].node_root, p)) return e;
+        if (node_inside<D>(sv, sv.entities()[e].node_root, p)) return e;
     return -1;
 }
 
@@ -219,61 +219,83 @@ __device__ __forceinline__ int chain_eval(const SceneView& sv, int op, int p0, i
     return n;
 }
 
-// Chain of exactly N plane-like leaves (half-spaces / hyperplanes: one hit each) -- cuboids (N = 6),
-// hypercuboids and 8-plane rooms (N = 8), wall sets (N = 4).  Same merge as chain_eval, but
-// organised for the GPU: all floating-point work (N roots, N hit points, N*(N-1) membership
-// tests, N*N distance comparisons) is straight-line and identical for every lane; the
-// data-dependent list bookkeeping then runs on integer bit masks only.  The list is a packed
-// array of 4-bit leaf indices.  Returns the list length; `t` receives the N root parameters.
-template <int D, int N>
-__device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, const Vec<D>& o, const Vec<D>& d,
-                                           bool first_only, double (&t)[N], unsigned long long& list_out) {
-    static_assert(N <= 8, "masks are packed N*N bits into 64");
-    // The host only routes chains here whose leaves are ALL half-spaces with signum = +-1.
-    const int np = sv.n_prims;
+// Chain of N <= 8 half-space leaves (one hit each, signum = +-1) -- cuboids (6), hypercuboids and
+// 8-plane rooms (8), wall sets (4).  Same merge as chain_eval, organised for the GPU:
+//   * all floating-point work (N roots, N*(N-1) membership tests) runs in ROLLED loops with tiny
+//     bodies: the first version of this kernel executed ~80 KB of distinct SASS per ray and was
+//     instruction-fetch bound (profiles/: stall_no_instruction); loop trip counts are identical
+//     for every lane, so nothing diverges;
+//   * the data-dependent list bookkeeping then runs on integer bit masks; root parameters live in
+//     a per-thread shared-memory scratch column (ts[i * ts_stride]) because the loops index them
+//     dynamically.
+// The list is a packed array of 4-bit leaf indices.  Returns the list length.
+constexpr int kPlaneChainMax = 8;
+template <int D>
+__device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, int N, const Vec<D>& o, const Vec<D>& d,
+                                           bool first_only, double* ts, int ts_stride, unsigned long long& list_out) {
+    const double* __restrict__ rec = sv.planes() + (size_t)p0 * kPlaneStride;
     unsigned exists = 0u;
-    Vec<D> pt[N]; // hit points, kept in registers so every plane is loaded once below
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < N; ++i) { // Hyperplane::intersect_linear, shape.rs:788-793
-        const Vec<D> nrm = load_vec<D>(sv.prim_v0 + p0 + i, np);
-        t[i] = -(dot(nrm, o) + sv.prim_s0[p0 + i]) / dot(nrm, d);
-        if (!(t[i] < 0.0)) exists |= 1u << i; // NaN and +inf pass
-        pt[i] = d * t[i] + o;
+        const double* r = rec + i * kPlaneStride;
+        Vec<D> nrm;
+#pragma unroll
+        for (int k = 0; k < D; ++k) nrm[k] = r[k];
+        const double t = -(dot(nrm, o) + r[4]) / dot(nrm, d);
+        ts[i * ts_stride] = t;
+        if (!(t < 0.0)) exists |= 1u << i; // NaN and +inf pass
     }
-    // inside[i] bit j: half-space j contains the hit point of leaf i (shape.rs:873-881):
-    // signum == (n.p + c).signum(), Rust signum = +-1 by sign bit, NaN for NaN
-    unsigned long long inside = 0ull, closer = 0ull;
+    // inside bit (i, j): half-space j contains the hit point of leaf i (shape.rs:873-881):
+    // signum == (n.p + c).signum(); Rust signum is +-1 by sign bit and NaN for NaN
+    unsigned long long inside = 0ull;
+    bool any = false;
+    const bool want_in = op == EUCL_CSG_INTERSECTION;
+    const unsigned all = (1u << N) - 1u;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+        const Vec<D> p = d * ts[i * ts_stride] + o;
+        unsigned row = 0u;
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {
+            const double* r = rec + j * kPlaneStride;
+            Vec<D> nrm;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const Vec<D> nrm = load_vec<D>(sv.prim_v0 + p0 + j, np);
-        const double c = sv.prim_s0[p0 + j];
-        const bool s_neg = sv.prim_s1[p0 + j] < 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (j == i) continue;
-            const double r = dot(nrm, pt[i]) + c;
-            const bool in = !isnan(r) && ((__double2hiint(r) < 0) == s_neg);
-            inside |= (unsigned long long)(in ? 1 : 0) << (i * N + j);
-            closer |= (unsigned long long)(t[i] < t[j] ? 1 : 0) << (i * N + j); // `a.distance < b.distance`
+            for (int k = 0; k < D; ++k) nrm[k] = r[k];
+            const double v = dot(nrm, p) + r[4];
+            const bool in = !isnan(v) && ((__double2hiint(v) < 0) == (r[5] < 0.0));
+            row |= (in ? 1u : 0u) << j;
         }
+        const unsigned others = all & ~(1u << i);
+        row &= others; // a leaf is never tested against itself
+        inside |= (unsigned long long)row << (i * N);
+        any = any || (((exists >> i) & 1u) && (want_in ? row == others : row == 0u));
+    }
+    // Every item of the final list was tested against ALL other leaves on its way (as `b` against
+    // the prefix, then as `a` against each later leaf) and kept only when inside (Intersection) /
+    // outside (Union) each time.  If no existing hit has such a row the list is empty: most rays
+    // miss most boxes and skip the replay.
+    if (!any) {
+        list_out = 0ull;
+        return 0;
     }
     // integer replay of the N-1 merges (IntersectionIterator / UnionIterator, shape.rs:212-340)
-    const bool is_and = op == EUCL_CSG_INTERSECTION;
     unsigned long long L = 0ull;
     int n = exists & 1u;
-#pragma unroll
+#pragma unroll 1
     for (int k = 1; k < N; ++k) {
         const unsigned prefix = (1u << k) - 1u;
         const unsigned mask_k = (unsigned)(inside >> (k * N)) & prefix;
-        const bool b_in = is_and ? mask_k == prefix : mask_k != 0u; // inside the fold of leaves 0..k-1
+        const bool b_in = want_in ? mask_k == prefix : mask_k != 0u; // inside the fold of leaves 0..k-1
         bool b_pending = (exists >> k) & 1u;
+        const double tk = ts[k * ts_stride];
         const int limit = (first_only && k == N - 1) ? 1 : N;
         unsigned long long T = 0ull;
         int ia = 0, m = 0;
         while (m < limit && (ia < n || b_pending)) {
             const bool has_a = ia < n, both = has_a && b_pending;
             const unsigned a = (unsigned)(L >> (4 * ia)) & 15u;
-            const bool take_a = has_a && (!b_pending || ((closer >> (a * N + k)) & 1ull));
+            // `a.distance < b.distance`: ties and NaN take b
+            const bool take_a = has_a && (!b_pending || ts[a * ts_stride] < tk);
             bool in;
             unsigned item;
             if (take_a) {
@@ -285,7 +307,7 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
                 in = b_in;
                 b_pending = false;
             }
-            if (is_and ? in : !in) {
+            if (want_in ? in : !in) {
                 T |= (unsigned long long)item << (4 * m);
                 ++m;
             } else if (!both) {
@@ -299,56 +321,12 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
     return n;
 }
 
-template <int N>
-__device__ __forceinline__ double select_t(const double (&t)[N], unsigned idx) {
-    double r = t[0];
-#pragma unroll
-    for (int i = 1; i < N; ++i) r = idx == (unsigned)i ? t[i] : r;
-    return r;
-}
-
-// Dispatch on the leaf count; returns false when N has no specialisation (generic chain_eval then).
-template <int D>
-__device__ __forceinline__ bool plane_chain_any(const SceneView& sv, int op, int p0, int count, const Vec<D>& o,
-                                                const Vec<D>& d, bool first_only, CHit* out, int& n_out) {
-    unsigned long long L = 0ull;
-    int n;
-    if (count == 2 * D) {
-        double t[2 * D];
-        n = plane_chain<D, 2 * D>(sv, op, p0, o, d, first_only, t, L);
-        for (int i = 0; i < n; ++i) {
-            const unsigned idx = (unsigned)(L >> (4 * i)) & 15u;
-            out[i] = CHit{select_t(t, idx), p0 + (int)idx, 0};
-        }
-    } else if (count == 4) {
-        double t[4];
-        n = plane_chain<D, 4>(sv, op, p0, o, d, first_only, t, L);
-        for (int i = 0; i < n; ++i) {
-            const unsigned idx = (unsigned)(L >> (4 * i)) & 15u;
-            out[i] = CHit{select_t(t, idx), p0 + (int)idx, 0};
-        }
-    } else {
-        return false;
-    }
-    n_out = n;
-    return true;
-}
-
-// A chain that is an entity's whole shape, generic leaves: only the first item is needed.
-template <int D>
-__device__ __noinline__ bool chain_first_generic(const SceneView& sv, int op, int p0, int count, const Vec<D>& o,
-                                                 const Vec<D>& d, CHit& out) {
-    CHit lists[2][CHAIN_ROOT_CAP];
-    const int c = chain_eval<D>(sv, op, p0, count, o, d, lists[0], lists[1], CHAIN_ROOT_CAP, true);
-    out = lists[0][0];
-    return c > 0;
-}
-
 // First item of the intersection stream of the macro program [first, root]
 // (ComposableShape::intersect_linear + the four merge iterators, shape.rs:204-584).
 template <int D>
-__device__ __noinline__ bool csg_first(const SceneView& sv, int first, int root, const Vec<D>& o, const Vec<D>& d, CHit& out) {
-    const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes);
+__device__ __forceinline__ bool csg_first(const SceneView& sv, int first, int root, const Vec<D>& o, const Vec<D>& d,
+                                          double* ts, int ts_stride, CHit& out) {
+    const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes());
     CHit arena[CSG_ARENA];
     int lstart[CSG_LIST_STACK], llen[CSG_LIST_STACK];
     int sp = 0, top = 0;
@@ -367,8 +345,16 @@ __device__ __noinline__ bool csg_first(const SceneView& sv, int first, int root,
         if (nd.kind == M_CHAIN) {
             const int count = nd.b & 0x3fff, cap = 2 * count;
             int c = 0;
-            if (!((nd.b & 0x4000) && plane_chain_any<D>(sv, nd.b >> 16, nd.a, count, o, d, n == root, arena + top, c)))
+            if ((nd.b & 0x4000) && count <= kPlaneChainMax) {
+                unsigned long long L = 0ull;
+                c = plane_chain<D>(sv, nd.b >> 16, nd.a, count, o, d, n == root, ts, ts_stride, L);
+                for (int i = 0; i < c; ++i) {
+                    const int idx = (int)((L >> (4 * i)) & 15ull);
+                    arena[top + i] = CHit{ts[idx * ts_stride], nd.a + idx, 0};
+                }
+            } else {
                 c = chain_eval<D>(sv, nd.b >> 16, nd.a, count, o, d, arena + top, arena + top + cap, cap, n == root);
+            }
             lstart[sp] = top;
             llen[sp] = c;
             ++sp;
@@ -471,30 +457,21 @@ struct ClosestHit {
 // asked for the FIRST item of its stream; a candidate replaces the current one only if it is
 // strictly closer (mod.rs:127-128), so a NaN distance wins only as the very first candidate.
 template <int D>
-__device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec<D>& o, const Vec<D>& d) {
+__device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, double* ts,
+                                                  int ts_stride) {
     ClosestHit best{-1, 0, 0, 0.0};
     for (int e = 0; e < sv.n_entities; ++e) {
-        const EuclEntity ent = sv.entities[e];
+        const EuclEntity ent = sv.entities()[e];
         if (ent.surface < 0) continue;
         CHit h;
         bool found;
-        const MNode root = reinterpret_cast<const MNode*>(sv.nodes)[ent.node_root];
+        const MNode root = reinterpret_cast<const MNode*>(sv.nodes())[ent.node_root];
         if (root.kind == M_PRIM) {
             double t0 = 0.0, t1 = 0.0;
             found = prim_roots<D>(sv, root.a, o, d, t0, t1) > 0;
             h = CHit{t0, root.a, 0};
-        } else if (root.kind == M_CHAIN) {
-            const int count = root.b & 0x3fff;
-            CHit first_hit[2 * D];
-            int c = 0;
-            if ((root.b & 0x4000) && plane_chain_any<D>(sv, root.b >> 16, root.a, count, o, d, true, first_hit, c)) {
-                found = c > 0;
-                h = first_hit[0];
-            } else {
-                found = chain_first_generic<D>(sv, root.b >> 16, root.a, count, o, d, h);
-            }
-        } else {
-            found = csg_first<D>(sv, ent.node_first, ent.node_root, o, d, h);
+        } else { // one call site: the evaluator (and the chain code inside it) exists once in the kernel
+            found = csg_first<D>(sv, ent.node_first, ent.node_root, o, d, ts, ts_stride, h);
         }
         if (found && (best.entity < 0 || best.t > h.t)) best = ClosestHit{e, h.prim, h.flags, h.t};
     }
@@ -507,13 +484,13 @@ template <int D>
 __device__ __forceinline__ void hit_geometry(const SceneView& sv, int prim, int flags, const Vec<D>& o, const Vec<D>& d,
                                              double t, Vec<D>& p, Vec<D>& nrm) {
     const int n = sv.n_prims;
-    const int kind = sv.prim_kind[prim];
+    const int kind = sv.prim_kind()[prim];
     if (kind == EUCL_PRIM_SPHERE) {
         p = o + d * t;
-        nrm = normalize(p - load_vec<D>(sv.prim_v0 + prim, n));
+        nrm = normalize(p - load_vec<D>(sv.prim_v0() + prim, n));
     } else if (kind == EUCL_PRIM_CYLINDER) {
-        Vec<D> center = load_vec<D>(sv.prim_v0 + prim, n);
-        Vec<D> axis = load_vec<D>(sv.prim_v1 + prim, n);
+        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
+        Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
         double t_first = t;
         if (flags & 1) { // the second hit reuses the axis point of the FIRST hit (shape.rs:999,1017)
             double r0 = 0.0, r1 = 0.0;
@@ -526,8 +503,8 @@ __device__ __forceinline__ void hit_geometry(const SceneView& sv, int prim, int 
         nrm = normalize(p - on_axis);
     } else {
         p = d * t + o;
-        nrm = load_vec<D>(sv.prim_v0 + prim, n);
-        if (kind == EUCL_PRIM_HALFSPACE) nrm = nrm * -sv.prim_s1[prim];
+        nrm = load_vec<D>(sv.prim_v0() + prim, n);
+        if (kind == EUCL_PRIM_HALFSPACE) nrm = nrm * -sv.prim_s1()[prim];
     }
     if (flags & 2) nrm = -nrm;
 }

@@ -14,8 +14,6 @@ namespace eucl {
 
 namespace {
 
-extern __shared__ __align__(16) unsigned char g_smem[];
-
 // resident CTAs per SM the register allocator must allow (occupancy hides the long FP64
 // div/sqrt dependency chains and the instruction-fetch bubbles of this branchy code)
 #ifndef EUCL_INTERSECT_MIN_BLOCKS
@@ -90,6 +88,13 @@ __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
     return Rgba{rg.x, rg.y, ba.x, ba.y};
 }
 
+// Per-thread scratch column for plane_chain (kPlaneChainMax doubles per thread, element i of thread
+// t at [i * blockDim.x + t]): lives in dynamic shared memory right after the staged scene.
+__device__ __forceinline__ double* plane_scratch(const uint8_t* __restrict__ blob) {
+    const int blob_bytes = reinterpret_cast<const SceneHeader*>(blob)->blob_bytes;
+    return reinterpret_cast<double*>(g_smem + scene_smem_bytes(blob_bytes)) + threadIdx.x;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared device logic (used by the wavefront kernels and the megakernel)
 
@@ -97,8 +102,8 @@ __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
 // and its orientation relative to the ray (mod.rs:114-125).
 template <int D>
 __device__ __forceinline__ int intersect_ray(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, bool& exiting, Vec<D>& p,
-                                             Vec<D>& n_raw) {
-    const ClosestHit h = closest_hit<D>(sv, o, d);
+                                             Vec<D>& n_raw, double* ts, int ts_stride) {
+    const ClosestHit h = closest_hit<D>(sv, o, d, ts, ts_stride);
     if (h.entity < 0) return -1;
     hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n_raw);
     exiting = angle_between(d, n_raw) < kFracPi2;
@@ -125,7 +130,7 @@ struct ShadeOut {
 template <int D>
 __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
                                           bool exiting, const Vec<D>& p, const Vec<D>& n_raw, ShadeOut<D>& out) {
-    const EuclSurface& sf = sv.surfaces[sv.entities[ent].surface];
+    const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
     const Vec<D> n_closer = exiting ? -n_raw : n_raw;
     // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
     const double ratio = fmax(fmin(reflection_ratio<D>(sf, dir, n_closer, exiting), 1.0), 0.0);
@@ -209,7 +214,7 @@ __device__ __forceinline__ Rgba checkerboard(int x, int y) { // mod.rs:387-395
 // material_at(camera location) is the same for every pixel of a frame: computed once.
 template <int D>
 __global__ void __launch_bounds__(32) k_camera_entity(const uint8_t* __restrict__ blob, FrameParams fp, Workspace ws) {
-    const SceneView& sv = stage_scene(blob, g_smem);
+    const SceneView& sv = stage_scene(blob);
     if (threadIdx.x == 0) {
         Vec<D> loc;
 #pragma unroll
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(32) k_camera_entity(const uint8_t* __restrict_
 template <int D>
 __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
                                                    Workspace ws, int32_t* __restrict__ hit_ids_out) {
-    const SceneView& sv = stage_scene(blob, g_smem);
+    const SceneView& sv = stage_scene(blob);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ws.count[0] = cp.n_pixels;
         ws.level_off[0] = 0;
@@ -255,7 +260,8 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
     const int off = ws.level_off[level], cnt = ws.count[level];
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.level_off[level + 1] = off + cnt;
     if (blockIdx.x * blockDim.x >= cnt) return;
-    const SceneView& sv = stage_scene(blob, g_smem);
+    const SceneView& sv = stage_scene(blob);
+    double* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cnt; base += stride) {
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
             Vec<D> o, d, p, n;
             load_ray<D>(ws, node, o, d);
             bool exiting = false;
-            ent = intersect_ray<D>(sv, o, d, exiting, p, n);
+            ent = intersect_ray<D>(sv, o, d, exiting, p, n, ts, (int)blockDim.x);
             ws.hit_ei[node] = make_int2(ent, exiting ? 1 : 0);
             if (ent >= 0) store_hit<D>(ws, node, p, n);
         }
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
     const int off = ws.level_off[level], cnt = ws.count[level];
     if (blockIdx.x * blockDim.x >= cnt) return;
     if (level > 0 && *ws.overflow) return; // set by an EARLIER kernel (level 0 always fits); see k_intersect
-    const SceneView& sv = stage_scene(blob, g_smem);
+    const SceneView& sv = stage_scene(blob);
     const bool last_level = level >= fp.max_depth; // depth 0: background without intersecting (mod.rs:157,183)
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
     const unsigned lane = threadIdx.x & 31u;
@@ -457,7 +463,8 @@ template <int D>
 __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
                                                        Workspace ws, uint8_t* __restrict__ out_rgb8,
                                                        int32_t* __restrict__ hit_ids_out) {
-    const SceneView& sv = stage_scene(blob, g_smem);
+    const SceneView& sv = stage_scene(blob);
+    double* ts = plane_scratch(blob);
     const int belongs_to = *ws.cam_entity;
     unsigned long long local_counts[kMegaMaxDepth + 1];
     for (int l = 0; l <= kMegaMaxDepth; ++l) local_counts[l] = 0ull;
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
             int ent = -1;
             bool exiting = false;
             Vec<D> p, n;
-            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n);
+            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n, ts, (int)blockDim.x);
             if (level == 0 && hit_ids_out) hit_ids_out[opix] = ent;
             if (ent < 0) {
                 val = mapped_color<D>(sv, sv.background, d);

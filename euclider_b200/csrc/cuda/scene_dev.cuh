@@ -26,36 +26,55 @@ struct SceneHeader {
     int32_t off_prim_kind, off_prim_v0, off_prim_v1, off_prim_s0, off_prim_s1;
     int32_t off_nodes, off_entities, off_materials, off_transforms, off_expr_ops;
     int32_t off_surfaces, off_color_ops, off_mapped, off_textures, off_tex_objects, off_perlin;
-    int32_t _pad[2];
+    int32_t off_planes;
+    int32_t _pad[1];
 };
 static_assert(sizeof(SceneHeader) % 16 == 0, "header must keep 16-byte alignment");
 
-// Pointers into the staged copy; lives in shared memory next to the blob.
+#if defined(__CUDACC__)
+// The one dynamic shared-memory array of every kernel: [SceneView][blob].  Declared here so that the
+// table accessors below are expressed relative to a __shared__ symbol and compile to LDS (going
+// through generic pointers stored in the view made them generic LD instructions).
+extern __shared__ __align__(16) unsigned char g_smem[];
+#endif
+
+// Byte offsets (from g_smem) of the staged tables; lives at the start of shared memory.
 struct SceneView {
     int dim, n_prims, n_nodes, n_entities, n_surfaces, background;
-    const int32_t* prim_kind;
-    const double* prim_v0;
-    const double* prim_v1;
-    const double* prim_s0;
-    const double* prim_s1;
-    const EuclNode* nodes;
-    const EuclEntity* entities;
-    const EuclMaterial* materials;
-    const EuclTransform* transforms;
-    const EuclExprOp* expr_ops;
-    const EuclSurface* surfaces;
-    const EuclColorOp* color_ops;
-    const EuclMappedTexture* mapped;
-    const EuclTexture* textures;
-    const cudaTextureObject_t* tex_objects;
-    const uint8_t* perlin;
+    uint32_t o_prim_kind, o_prim_v0, o_prim_v1, o_prim_s0, o_prim_s1, o_planes, o_nodes, o_entities, o_materials,
+        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin;
+#if defined(__CUDACC__)
+#define EUCL_TABLE(type, name) \
+    __device__ __forceinline__ const type* name() const { return reinterpret_cast<const type*>(g_smem + o_##name); }
+    EUCL_TABLE(int32_t, prim_kind)
+    EUCL_TABLE(double, prim_v0)
+    EUCL_TABLE(double, prim_v1)
+    EUCL_TABLE(double, prim_s0)
+    EUCL_TABLE(double, prim_s1)
+    EUCL_TABLE(double, planes) // AoS copy of the primitives: kPlaneStride doubles each, [v0[0..3], s0, s1]
+    EUCL_TABLE(EuclNode, nodes)
+    EUCL_TABLE(EuclEntity, entities)
+    EUCL_TABLE(EuclMaterial, materials)
+    EUCL_TABLE(EuclTransform, transforms)
+    EUCL_TABLE(EuclExprOp, expr_ops)
+    EUCL_TABLE(EuclSurface, surfaces)
+    EUCL_TABLE(EuclColorOp, color_ops)
+    EUCL_TABLE(EuclMappedTexture, mapped)
+    EUCL_TABLE(EuclTexture, textures)
+    EUCL_TABLE(cudaTextureObject_t, tex_objects)
+    EUCL_TABLE(uint8_t, perlin)
+#undef EUCL_TABLE
+#endif
 };
+constexpr int kPlaneStride = 6; // doubles per record of the AoS primitive table (48 B, 16-byte aligned)
 
-// Cooperative copy of the blob into shared memory + view construction.  `smem` must be 16-byte
-// aligned and hold sizeof(SceneView) rounded to 16 + blob_bytes.
-__device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restrict__ blob, unsigned char* smem) {
-    SceneView* view = reinterpret_cast<SceneView*>(smem);
-    unsigned char* dst = smem + ((sizeof(SceneView) + 15) & ~size_t(15));
+#if defined(__CUDACC__)
+// Cooperative copy of the blob into shared memory + view construction.  g_smem must hold
+// scene_smem_bytes(blob_bytes).
+__device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restrict__ blob) {
+    SceneView* view = reinterpret_cast<SceneView*>(g_smem);
+    const uint32_t base = (uint32_t)((sizeof(SceneView) + 15) & ~size_t(15));
+    unsigned char* dst = g_smem + base;
     const SceneHeader* gh = reinterpret_cast<const SceneHeader*>(blob);
     const int n16 = gh->blob_bytes >> 4;
     const uint4* src4 = reinterpret_cast<const uint4*>(blob);
@@ -70,26 +89,28 @@ __device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restric
         view->n_entities = h->n_entities;
         view->n_surfaces = h->n_surfaces;
         view->background = h->background;
-        view->prim_kind = reinterpret_cast<const int32_t*>(dst + h->off_prim_kind);
-        view->prim_v0 = reinterpret_cast<const double*>(dst + h->off_prim_v0);
-        view->prim_v1 = reinterpret_cast<const double*>(dst + h->off_prim_v1);
-        view->prim_s0 = reinterpret_cast<const double*>(dst + h->off_prim_s0);
-        view->prim_s1 = reinterpret_cast<const double*>(dst + h->off_prim_s1);
-        view->nodes = reinterpret_cast<const EuclNode*>(dst + h->off_nodes);
-        view->entities = reinterpret_cast<const EuclEntity*>(dst + h->off_entities);
-        view->materials = reinterpret_cast<const EuclMaterial*>(dst + h->off_materials);
-        view->transforms = reinterpret_cast<const EuclTransform*>(dst + h->off_transforms);
-        view->expr_ops = reinterpret_cast<const EuclExprOp*>(dst + h->off_expr_ops);
-        view->surfaces = reinterpret_cast<const EuclSurface*>(dst + h->off_surfaces);
-        view->color_ops = reinterpret_cast<const EuclColorOp*>(dst + h->off_color_ops);
-        view->mapped = reinterpret_cast<const EuclMappedTexture*>(dst + h->off_mapped);
-        view->textures = reinterpret_cast<const EuclTexture*>(dst + h->off_textures);
-        view->tex_objects = reinterpret_cast<const cudaTextureObject_t*>(dst + h->off_tex_objects);
-        view->perlin = reinterpret_cast<const uint8_t*>(dst + h->off_perlin);
+        view->o_prim_kind = base + h->off_prim_kind;
+        view->o_prim_v0 = base + h->off_prim_v0;
+        view->o_prim_v1 = base + h->off_prim_v1;
+        view->o_prim_s0 = base + h->off_prim_s0;
+        view->o_prim_s1 = base + h->off_prim_s1;
+        view->o_planes = base + h->off_planes;
+        view->o_nodes = base + h->off_nodes;
+        view->o_entities = base + h->off_entities;
+        view->o_materials = base + h->off_materials;
+        view->o_transforms = base + h->off_transforms;
+        view->o_expr_ops = base + h->off_expr_ops;
+        view->o_surfaces = base + h->off_surfaces;
+        view->o_color_ops = base + h->off_color_ops;
+        view->o_mapped = base + h->off_mapped;
+        view->o_textures = base + h->off_textures;
+        view->o_tex_objects = base + h->off_tex_objects;
+        view->o_perlin = base + h->off_perlin;
     }
     __syncthreads();
     return *view;
 }
+#endif
 
 __host__ __device__ inline size_t scene_smem_bytes(int blob_bytes) {
     return ((sizeof(SceneView) + 15) & ~size_t(15)) + (size_t)blob_bytes;

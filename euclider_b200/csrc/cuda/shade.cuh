@@ -218,15 +218,15 @@ __device__ __forceinline__ Rgba fetch_texel(cudaTextureObject_t tex, const EuclT
 template <int D>
 __device__ __noinline__ Rgba mapped_color(const SceneView& sv, int mapped, const Vec<D>& point) {
     if (mapped < 0) return Rgba{0.0, 0.0, 0.0, 0.0}; // MappedTextureTransparent
-    const EuclMappedTexture mt = sv.mapped[mapped];
+    const EuclMappedTexture mt = sv.mapped()[mapped];
     Vec<3> p;
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
     p = normalize(p);
     const double u = 0.5 + dm_atan2(p[1], p[0]) / (2.0 * kPi);
     const double v = 0.5 - dm_asin(p[2]) / kPi;
-    const EuclTexture t = sv.textures[mt.texture];
-    const cudaTextureObject_t tex = sv.tex_objects[mt.texture];
+    const EuclTexture t = sv.textures()[mt.texture];
+    const cudaTextureObject_t tex = sv.tex_objects()[mt.texture];
     const double width = (double)t.width, height = (double)t.height;
     if (mt.filter == EUCL_TEX_NEAREST) {
         double x = floor(u * width), y = floor(v * height);
@@ -258,7 +258,7 @@ __device__ __noinline__ double eval_expr(const SceneView& sv, int first, int len
     double st[16];
     int sp = 0;
     for (int i = first; i < first + len; ++i) {
-        const EuclExprOp o = sv.expr_ops[i];
+        const EuclExprOp o = sv.expr_ops()[i];
         if (o.op == EUCL_EX_CONST) {
             st[sp++] = o.value;
         } else if (o.op == EUCL_EX_VAR) {
@@ -322,16 +322,16 @@ __device__ __noinline__ void apply_transform(const SceneView& sv, const EuclTran
 // Material::enter (Vacuum: no-op, material.rs:43-49; LinearSpace: forward transforms in order, :133-137)
 template <int D>
 __device__ __forceinline__ void material_enter(const SceneView& sv, int entity, Vec<D>& dir) {
-    const EuclMaterial m = sv.materials[sv.entities[entity].material];
+    const EuclMaterial m = sv.materials()[sv.entities()[entity].material];
     if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
-    for (int k = 0; k < m.n_transforms; ++k) apply_transform<D>(sv, sv.transforms[m.transform_first + k], false, dir);
+    for (int k = 0; k < m.n_transforms; ++k) apply_transform<D>(sv, sv.transforms()[m.transform_first + k], false, dir);
 }
 // Material::exit (LinearSpace: inverse transforms in reverse order, material.rs:139-142,156-162)
 template <int D>
 __device__ __forceinline__ void material_exit(const SceneView& sv, int entity, Vec<D>& dir) {
-    const EuclMaterial m = sv.materials[sv.entities[entity].material];
+    const EuclMaterial m = sv.materials()[sv.entities()[entity].material];
     if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
-    for (int k = m.n_transforms - 1; k >= 0; --k) apply_transform<D>(sv, sv.transforms[m.transform_first + k], true, dir);
+    for (int k = m.n_transforms - 1; k >= 0; --k) apply_transform<D>(sv, sv.transforms()[m.transform_first + k], true, dir);
 }
 
 // --- surface providers -------------------------------------------------------------------------
@@ -466,7 +466,7 @@ __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurfac
     Rgba stack[8];
     int sp = 0;
     for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
-        const EuclColorOp& op = sv.color_ops[i];
+        const EuclColorOp& op = sv.color_ops()[i];
         const int code = op.op;
         if (code == EUCL_COL_UNIFORM) { // surface.rs:425-429
             stack[sp++] = Rgba{op.f[0], op.f[1], op.f[2], op.f[3]};
@@ -489,7 +489,7 @@ __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurfac
         } else if (code == EUCL_COL_PERLIN_HUE) { // d3/entity/surface.rs:22-40
             const double size = op.f[0], speed = op.f[1];
             const double point[4] = {location[0] / size, location[1] / size, location[2] / size, time_millis * speed};
-            stack[sp++] = hue_to_rgba(perlin4(sv.perlin, point) * 360.0);
+            stack[sp++] = hue_to_rgba(perlin4(sv.perlin(), point) * 360.0);
         } else if (code == EUCL_COL_TEXTURE) { // surface.rs:536-542
             stack[sp++] = mapped_color<D>(sv, op.i0, location);
         } else { // EUCL_COL_BLEND, surface.rs:295-307
