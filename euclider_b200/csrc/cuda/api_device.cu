@@ -188,6 +188,113 @@ struct MacroBuilder {
         out.push_back(MNode{M_OP, nd.op, 0, first});
     }
 
+    // Conservative bounding spheres (intersect.cuh: Bound) of macro range [first, root]: for each
+    // node a sphere containing every point the node's shape can contain and hence every hit its
+    // stream can emit (rules in DESIGN.md, "ray/bound culling").  r2 < 0: unbounded.
+    void compute_bounds(int first, int root, std::vector<Bound>* bounds) const {
+        const int D = f.dim;
+        auto none = [] {
+            Bound b{};
+            b.r2 = -1.0;
+            return b;
+        };
+        auto radius = [](const Bound& b) { return std::sqrt(b.r2); };
+        auto enclose = [&](const Bound& x, const Bound& y) { // sphere around two spheres
+            if (x.r2 < 0 || y.r2 < 0) return none();
+            double dist2 = 0;
+            for (int k = 0; k < D; ++k) dist2 += (x.c[k] - y.c[k]) * (x.c[k] - y.c[k]);
+            Bound b{};
+            for (int k = 0; k < D; ++k) b.c[k] = 0.5 * (x.c[k] + y.c[k]);
+            const double r = 0.5 * std::sqrt(dist2) + std::max(radius(x), radius(y));
+            b.r2 = r * r;
+            return b;
+        };
+        auto smaller = [&](const Bound& x, const Bound& y) {
+            if (x.r2 < 0) return y;
+            if (y.r2 < 0) return x;
+            return x.r2 <= y.r2 ? x : y;
+        };
+        auto prim_bound = [&](int prim) {
+            const EuclPrim& p = f.prims[prim];
+            Bound b = none();
+            if (p.kind == EUCL_PRIM_SPHERE && std::isfinite(p.s0)) {
+                for (int k = 0; k < D; ++k) b.c[k] = p.v0[k];
+                b.r2 = p.s0 * p.s0;
+            }
+            return b;
+        };
+        auto chain_bound = [&](const MNode& nd) {
+            const int count = nd.b & 0x3fff, op = nd.b >> 16;
+            if (op == EUCL_CSG_UNION) {
+                Bound acc = prim_bound(nd.a);
+                for (int i = 1; i < count; ++i) acc = enclose(acc, prim_bound(nd.a + i));
+                return acc;
+            }
+            // Intersection: the axis-aligned half-spaces of the chain may box the region in
+            double lo[EUCL_MAX_DIM], hi[EUCL_MAX_DIM];
+            for (int k = 0; k < D; ++k) {
+                lo[k] = -INFINITY;
+                hi[k] = INFINITY;
+            }
+            Bound best = none();
+            for (int i = 0; i < count; ++i) {
+                const EuclPrim& p = f.prims[nd.a + i];
+                best = smaller(best, prim_bound(nd.a + i));
+                if (p.kind != EUCL_PRIM_HALFSPACE || !(p.s1 == 1.0 || p.s1 == -1.0)) continue;
+                int axis = -1, nonzero = 0;
+                for (int k = 0; k < D; ++k)
+                    if (p.v0[k] != 0.0) {
+                        axis = k;
+                        ++nonzero;
+                    }
+                if (nonzero != 1 || !std::isfinite(p.v0[axis]) || !std::isfinite(p.s0)) continue;
+                const double edge = -p.s0 / p.v0[axis]; // region: signum * (n_k x_k + c) >= 0
+                if (p.s1 * p.v0[axis] > 0) lo[axis] = std::max(lo[axis], edge);
+                else hi[axis] = std::min(hi[axis], edge);
+            }
+            bool boxed = true;
+            for (int k = 0; k < D; ++k) boxed = boxed && std::isfinite(lo[k]) && std::isfinite(hi[k]) && lo[k] <= hi[k];
+            if (boxed) {
+                Bound b{};
+                double r2 = 0;
+                for (int k = 0; k < D; ++k) {
+                    b.c[k] = 0.5 * (lo[k] + hi[k]);
+                    r2 += 0.25 * (hi[k] - lo[k]) * (hi[k] - lo[k]);
+                }
+                b.r2 = r2;
+                best = smaller(best, b);
+            }
+            return best;
+        };
+        std::vector<Bound> stack;
+        for (int n = first; n <= root; ++n) {
+            const MNode& nd = out[(size_t)n];
+            Bound b;
+            if (nd.kind == M_PRIM) {
+                b = prim_bound(nd.a);
+            } else if (nd.kind == M_CHAIN) {
+                b = chain_bound(nd);
+            } else {
+                const Bound y = stack.back();
+                stack.pop_back();
+                const Bound x = stack.back();
+                stack.pop_back();
+                b = nd.a == EUCL_CSG_INTERSECTION ? smaller(x, y) : nd.a == EUCL_CSG_COMPLEMENT ? x : enclose(x, y);
+            }
+            stack.push_back(b);
+            // inflate: the culling test must stay conservative under rounding (errors ~1e-13 relative)
+            Bound stored = b;
+            if (stored.r2 >= 0) {
+                double cmax = 1.0;
+                for (int k = 0; k < D; ++k) cmax = std::max(cmax, std::fabs(stored.c[k]));
+                const double r = std::sqrt(stored.r2) * (1.0 + 1e-6) + 1e-7 * cmax;
+                stored.r2 = r * r;
+                if (!std::isfinite(stored.r2)) stored.r2 = -1.0;
+            }
+            (*bounds)[(size_t)n] = stored;
+        }
+    }
+
     // Worst-case arena use of the device evaluator (csg_first) for macro range [first, root]
     bool fits(int first, int root, int* peak_out, int* depth_out) const {
         std::vector<int> lens;
@@ -388,8 +495,14 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
                                                   std::to_string(depth) + ")");
         dev_entities[(size_t)e] = de;
     }
+    std::vector<Bound> bounds(mb.out.size());
+    for (int e = 0; e < flat->n_entities; ++e)
+        mb.compute_bounds(dev_entities[(size_t)e].node_first, dev_entities[(size_t)e].node_root, &bounds);
+    if (!env_int("EUCL_BOUND_CULL", 1))
+        for (auto& b : bounds) b.r2 = -1.0;
     h.n_nodes = (int)mb.out.size();
     h.off_nodes = w.put(mb.out.data(), mb.out.size());
+    h.off_bounds = w.put(bounds.data(), bounds.size());
     h.off_entities = w.put(dev_entities.data(), dev_entities.size());
     h.off_materials = w.put(flat->materials, (size_t)flat->n_materials);
     h.off_transforms = w.put(flat->transforms, (size_t)flat->n_transforms);

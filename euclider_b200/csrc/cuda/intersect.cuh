@@ -178,6 +178,23 @@ __device__ __noinline__ int material_at(const SceneView& sv, const Vec<D>& p) {
     return -1;
 }
 
+// Ray / bounding-sphere rejection.  A macro node's Bound (built on the host, inflated by 1e-6)
+// contains every point its shape can contain, hence every hit its stream can emit: an emitted hit
+// is a boundary point of the shape -- it was tested inside all sibling leaves -- up to rounding of
+// ~1e-13, far inside the inflation.  If the half-line o + t d, t >= 0, stays outside the sphere,
+// the node's hit list is empty and the whole evaluation is skipped.  NaN anywhere makes every
+// comparison false: such rays are never culled and take the exact path.
+template <int D>
+__device__ __forceinline__ bool ray_misses(const Bound& bnd, const Vec<D>& o, const Vec<D>& d, double dd) {
+    if (!(bnd.r2 >= 0.0)) return false;
+    Vec<D> rel;
+#pragma unroll
+    for (int k = 0; k < D; ++k) rel[k] = o[k] - bnd.c[k];
+    const double b = dot(d, rel);
+    const double c = dot(rel, rel) - bnd.r2;
+    return (b * b - dd * c < 0.0) || (c > 0.0 && b > 0.0);
+}
+
 // Hit list of a chain macro node, "up to the first None", written to L (capacity cap; T is scratch
 // of the same size).  Step k merges the list so far (stream A) with the hits of leaf k (stream B)
 // exactly like IntersectionIterator / UnionIterator (shape.rs:212-340):
@@ -327,6 +344,7 @@ template <int D>
 __device__ __forceinline__ bool csg_first(const SceneView& sv, int first, int root, const Vec<D>& o, const Vec<D>& d,
                                           double* ts, int ts_stride, CHit& out) {
     const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes());
+    const double dd = dot(d, d);
     CHit arena[CSG_ARENA];
     int lstart[CSG_LIST_STACK], llen[CSG_LIST_STACK];
     int sp = 0, top = 0;
@@ -345,7 +363,9 @@ __device__ __forceinline__ bool csg_first(const SceneView& sv, int first, int ro
         if (nd.kind == M_CHAIN) {
             const int count = nd.b & 0x3fff, cap = 2 * count;
             int c = 0;
-            if ((nd.b & 0x4000) && count <= kPlaneChainMax) {
+            if (ray_misses<D>(sv.bounds()[n], o, d, dd)) {
+                c = 0; // the chain's region is out of the ray's reach: empty list
+            } else if ((nd.b & 0x4000) && count <= kPlaneChainMax) {
                 unsigned long long L = 0ull;
                 c = plane_chain<D>(sv, nd.b >> 16, nd.a, count, o, d, n == root, ts, ts_stride, L);
                 for (int i = 0; i < c; ++i) {
@@ -460,12 +480,14 @@ template <int D>
 __device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, double* ts,
                                                   int ts_stride) {
     ClosestHit best{-1, 0, 0, 0.0};
+    const double dd = dot(d, d);
     for (int e = 0; e < sv.n_entities; ++e) {
         const EuclEntity ent = sv.entities()[e];
         if (ent.surface < 0) continue;
         CHit h;
         bool found;
         const MNode root = reinterpret_cast<const MNode*>(sv.nodes())[ent.node_root];
+        if (root.kind != M_PRIM && ray_misses<D>(sv.bounds()[ent.node_root], o, d, dd)) continue; // no hit can come from this entity
         if (root.kind == M_PRIM) {
             double t0 = 0.0, t1 = 0.0;
             found = prim_roots<D>(sv, root.a, o, d, t0, t1) > 0;

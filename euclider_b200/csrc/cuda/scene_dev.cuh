@@ -26,10 +26,16 @@ struct SceneHeader {
     int32_t off_prim_kind, off_prim_v0, off_prim_v1, off_prim_s0, off_prim_s1;
     int32_t off_nodes, off_entities, off_materials, off_transforms, off_expr_ops;
     int32_t off_surfaces, off_color_ops, off_mapped, off_textures, off_tex_objects, off_perlin;
-    int32_t off_planes;
-    int32_t _pad[1];
+    int32_t off_planes, off_bounds;
 };
 static_assert(sizeof(SceneHeader) % 16 == 0, "header must keep 16-byte alignment");
+
+// Conservative bounding sphere of a macro CSG node (r2 < 0: unbounded); see intersect.cuh: ray_misses.
+struct Bound {
+    double c[EUCL_MAX_DIM];
+    double r2;
+    double _pad;
+};
 
 #if defined(__CUDACC__)
 // The one dynamic shared-memory array of every kernel: [SceneView][blob].  Declared here so that the
@@ -42,7 +48,7 @@ extern __shared__ __align__(16) unsigned char g_smem[];
 struct SceneView {
     int dim, n_prims, n_nodes, n_entities, n_surfaces, background;
     uint32_t o_prim_kind, o_prim_v0, o_prim_v1, o_prim_s0, o_prim_s1, o_planes, o_nodes, o_entities, o_materials,
-        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin;
+        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin, o_bounds;
 #if defined(__CUDACC__)
 #define EUCL_TABLE(type, name) \
     __device__ __forceinline__ const type* name() const { return reinterpret_cast<const type*>(g_smem + o_##name); }
@@ -63,6 +69,7 @@ struct SceneView {
     EUCL_TABLE(EuclTexture, textures)
     EUCL_TABLE(cudaTextureObject_t, tex_objects)
     EUCL_TABLE(uint8_t, perlin)
+    EUCL_TABLE(Bound, bounds) // one per macro CSG node
 #undef EUCL_TABLE
 #endif
 };
@@ -106,6 +113,7 @@ __device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restric
         view->o_textures = base + h->off_textures;
         view->o_tex_objects = base + h->off_tex_objects;
         view->o_perlin = base + h->off_perlin;
+        view->o_bounds = base + h->off_bounds;
     }
     __syncthreads();
     return *view;
