@@ -579,7 +579,7 @@ void frame_params(const EuclCamera& cam, const EuclRenderOpts& o, FrameParams* f
 }
 
 size_t arena_bytes(int dim, size_t cap) {
-    size_t per = (size_t)dim * 16 * 2 + 4 + 8 + sizeof(NodeMeta) + 32;
+    size_t per = (size_t)dim * 16 * 2 + 4 + sizeof(HitInfo) + sizeof(NodeMeta) + 32;
     return per * cap + 16 * 16;
 }
 
@@ -597,7 +597,7 @@ Workspace carve(EuclScene* s, int dim, int cap) {
     ws.res_rg = (double2*)take((size_t)16 * cap);
     ws.res_ba = (double2*)take((size_t)16 * cap);
     ws.meta = (NodeMeta*)take(sizeof(NodeMeta) * (size_t)cap);
-    ws.hit_ei = (int2*)take((size_t)8 * cap);
+    ws.hit_ei = (HitInfo*)take(sizeof(HitInfo) * (size_t)cap);
     ws.ray_cur = (int32_t*)take((size_t)4 * cap);
     int32_t* small = (int32_t*)s->small.ptr;
     ws.count = small + SmallLayout::count;
@@ -626,7 +626,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     EUCL_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (my_rows > 0) {
         // chunking: whole local rows, about EUCL_CHUNK_PIXELS primaries per chunk
-        const long long chunk_pixels_target = std::max(1, env_int("EUCL_CHUNK_PIXELS", 1 << 21));
+        const long long chunk_pixels_target = std::max(1, env_int("EUCL_CHUNK_PIXELS", 1 << 22));
         int rows_per_chunk = (int)std::max<long long>(1, chunk_pixels_target / width);
         rows_per_chunk = std::min<int>(rows_per_chunk, (int)my_rows);
         const long long chunk_pixels = (long long)rows_per_chunk * width;

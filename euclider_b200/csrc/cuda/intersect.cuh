@@ -173,8 +173,18 @@ __device__ __noinline__ bool node_inside(const SceneView& sv, int n, const Vec<D
 // Universe::material_at (mod.rs:229-251): first entity in list order containing the point
 template <int D>
 __device__ __noinline__ int material_at(const SceneView& sv, const Vec<D>& p) {
-    for (int e = 0; e < sv.n_entities; ++e)
-        if (node_inside<D>(sv, sv.entities()[e].node_root, p)) return e;
+    for (int e = 0; e < sv.n_entities; ++e) {
+        const int root = sv.entities()[e].node_root;
+        // a point outside the (inflated) bounding sphere of the shape cannot be inside it; NaN -> not skipped
+        const Bound& bnd = sv.bounds()[root];
+        if (bnd.r2 >= 0.0) {
+            double dist2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) dist2 += (p[k] - bnd.c[k]) * (p[k] - bnd.c[k]);
+            if (dist2 > bnd.r2) continue;
+        }
+        if (node_inside<D>(sv, root, p)) return e;
+    }
     return -1;
 }
 
@@ -236,6 +246,41 @@ __device__ __forceinline__ int chain_eval(const SceneView& sv, int op, int p0, i
     return n;
 }
 
+// Membership rows of G consecutive hit points of a plane chain against all N planes.
+template <int D, int G>
+__device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N, const Vec<D>& o, const Vec<D>& d,
+                                           const double* ts, int ts_stride, int i0, unsigned long long& inside) {
+    Vec<D> p[G];
+    unsigned rows[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int i = min(i0 + g, N - 1); // padding lanes of the last group repeat a valid point
+        p[g] = d * ts[i * ts_stride] + o;
+        rows[g] = 0u;
+    }
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        const double* r = rec + j * kPlaneStride;
+        Vec<D> nrm;
+#pragma unroll
+        for (int k = 0; k < D; ++k) nrm[k] = r[k];
+        const double c = r[4];
+        const bool s_neg = r[5] < 0.0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const double v = dot(nrm, p[g]) + c;
+            const bool in = !isnan(v) && ((__double2hiint(v) < 0) == s_neg);
+            rows[g] |= (in ? 1u : 0u) << j;
+        }
+    }
+    const unsigned all = (1u << N) - 1u;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int i = i0 + g;
+        if (i < N) inside |= (unsigned long long)(rows[g] & all & ~(1u << i)) << (i * N); // never against itself
+    }
+}
+
 // Chain of N <= 8 half-space leaves (one hit each, signum = +-1) -- cuboids (6), hypercuboids and
 // 8-plane rooms (8), wall sets (4).  Same merge as chain_eval, organised for the GPU:
 //   * all floating-point work (N roots, N*(N-1) membership tests) runs in ROLLED loops with tiny
@@ -263,28 +308,22 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         if (!(t < 0.0)) exists |= 1u << i; // NaN and +inf pass
     }
     // inside bit (i, j): half-space j contains the hit point of leaf i (shape.rs:873-881):
-    // signum == (n.p + c).signum(); Rust signum is +-1 by sign bit and NaN for NaN
+    // signum == (n.p + c).signum(); Rust signum is +-1 by sign bit and NaN for NaN.
+    // Hit points are processed in groups of G kept in registers while a rolled loop walks the
+    // planes, so each plane record is loaded once per group and the loop body stays small.
     unsigned long long inside = 0ull;
-    bool any = false;
     const bool want_in = op == EUCL_CSG_INTERSECTION;
     const unsigned all = (1u << N) - 1u;
+    if (N % 3 == 0) {
+        for (int i0 = 0; i0 < N; i0 += 3) plane_rows<D, 3>(rec, N, o, d, ts, ts_stride, i0, inside);
+    } else {
+        for (int i0 = 0; i0 < N; i0 += 4) plane_rows<D, 4>(rec, N, o, d, ts, ts_stride, i0, inside);
+    }
+    bool any = false;
 #pragma unroll 1
     for (int i = 0; i < N; ++i) {
-        const Vec<D> p = d * ts[i * ts_stride] + o;
-        unsigned row = 0u;
-#pragma unroll 1
-        for (int j = 0; j < N; ++j) {
-            const double* r = rec + j * kPlaneStride;
-            Vec<D> nrm;
-#pragma unroll
-            for (int k = 0; k < D; ++k) nrm[k] = r[k];
-            const double v = dot(nrm, p) + r[4];
-            const bool in = !isnan(v) && ((__double2hiint(v) < 0) == (r[5] < 0.0));
-            row |= (in ? 1u : 0u) << j;
-        }
         const unsigned others = all & ~(1u << i);
-        row &= others; // a leaf is never tested against itself
-        inside |= (unsigned long long)row << (i * N);
+        const unsigned row = (unsigned)(inside >> (i * N)) & others;
         any = any || (((exists >> i) & 1u) && (want_in ? row == others : row == 0u));
     }
     // Every item of the final list was tested against ALL other leaves on its way (as `b` against

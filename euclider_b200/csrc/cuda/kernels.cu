@@ -20,7 +20,7 @@ namespace {
 #define EUCL_INTERSECT_MIN_BLOCKS 4
 #endif
 #ifndef EUCL_SHADE_MIN_BLOCKS
-#define EUCL_SHADE_MIN_BLOCKS 3
+#define EUCL_SHADE_MIN_BLOCKS 4
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -102,11 +102,12 @@ __device__ __forceinline__ double* plane_scratch(const uint8_t* __restrict__ blo
 // and its orientation relative to the ray (mod.rs:114-125).
 template <int D>
 __device__ __forceinline__ int intersect_ray(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, bool& exiting, Vec<D>& p,
-                                             Vec<D>& n_raw, double* ts, int ts_stride) {
+                                             Vec<D>& n_raw, double& cos_raw, double* ts, int ts_stride) {
     const ClosestHit h = closest_hit<D>(sv, o, d, ts, ts_stride);
     if (h.entity < 0) return -1;
     hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n_raw);
-    exiting = angle_between(d, n_raw) < kFracPi2;
+    cos_raw = angle_cos(d, n_raw);
+    exiting = angle_from_cos(cos_raw) < kFracPi2;
     return h.entity;
 }
 
@@ -129,11 +130,15 @@ struct ShadeOut {
 // (surface.rs:62-162): decides which children exist and where they start.
 template <int D>
 __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
-                                          bool exiting, const Vec<D>& p, const Vec<D>& n_raw, ShadeOut<D>& out) {
+                                          bool exiting, double cos_raw, const Vec<D>& p, const Vec<D>& n_raw,
+                                          ShadeOut<D>& out) {
     const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
     const Vec<D> n_closer = exiting ? -n_raw : n_raw;
+    const double cos_closer = exiting ? -cos_raw : cos_raw;
+    const bool needs_theta = sf.ratio_op == EUCL_RATIO_FRESNEL || sf.thr_op == EUCL_THR_SNELL;
+    const double from_theta = needs_theta ? angle_from_cos(-cos_closer) : 0.0;
     // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
-    const double ratio = fmax(fmin(reflection_ratio<D>(sf, dir, n_closer, exiting), 1.0), 0.0);
+    const double ratio = fmax(fmin(reflection_ratio<D>(sf, from_theta, exiting), 1.0), 0.0);
     out.ratio = ratio;
     out.q = 0u;
     out.flags = 0u;
@@ -141,7 +146,7 @@ __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_milli
     out.r_emit = false;
     bool have_t = false;
     if (!(ratio >= 1.0)) { // get_intersection_color
-        const Rgba sc = surface_color<D>(sv, sf, dir, p, n_raw, n_closer, time_millis);
+        const Rgba sc = surface_color<D>(sv, sf, dir, p, n_raw, cos_raw, cos_closer, time_millis);
         const unsigned q = to_pixel4(sc);
         out.q = q;
         if ((q >> 24) == 255u) {
@@ -149,7 +154,7 @@ __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_milli
             out.flags |= NODE_HAS_SC;
             have_t = true;
         } else {
-            Vec<D> td = threshold_direction<D>(sf, dir, n_closer, exiting);
+            Vec<D> td = threshold_direction<D>(sf, dir, n_closer, exiting, from_theta);
             const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
             const int dest = exiting ? material_at<D>(sv, new_origin) : ent;
             if (dest >= 0) {
@@ -273,8 +278,9 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
             Vec<D> o, d, p, n;
             load_ray<D>(ws, node, o, d);
             bool exiting = false;
-            ent = intersect_ray<D>(sv, o, d, exiting, p, n, ts, (int)blockDim.x);
-            ws.hit_ei[node] = make_int2(ent, exiting ? 1 : 0);
+            double cos_raw = 0.0;
+            ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, ts, (int)blockDim.x);
+            ws.hit_ei[node] = HitInfo{ent, exiting ? 1 : 0, cos_raw};
             if (ent >= 0) store_hit<D>(ws, node, p, n);
         }
         if (ws.n_bins > 1) {
@@ -340,19 +346,19 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
             Vec<D> o, d;
             load_ray<D>(ws, node, o, d);
             const int cur = ws.ray_cur[node];
-            const int2 ei = last_level ? make_int2(-1, 0) : ws.hit_ei[node];
+            const HitInfo ei = last_level ? HitInfo{-1, 0, 0.0} : ws.hit_ei[node];
             if (level == 0 && hit_ids_out) {
                 const int local_row = cp.local_row0 + i / fp.width;
                 const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
-                hit_ids_out[(size_t)orow * fp.width + i % fp.width] = ei.x;
+                hit_ids_out[(size_t)orow * fp.width + i % fp.width] = ei.entity;
             }
-            if (ei.x < 0) {
+            if (ei.entity < 0) {
                 store_res(ws, node, mapped_color<D>(sv, sv.background, d)); // background.get_color(direction.to_point())
                 ws.meta[node] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF};
             } else {
                 Vec<D> p, n;
                 load_hit<D>(ws, node, p, n);
-                shade_hit<D>(sv, fp.time_millis, d, cur, ei.x, ei.y != 0, p, n, so);
+                shade_hit<D>(sv, fp.time_millis, d, cur, ei.entity, ei.exiting != 0, ei.cos_raw, p, n, so);
                 shaded = true;
             }
         }
@@ -494,13 +500,14 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
             int ent = -1;
             bool exiting = false;
             Vec<D> p, n;
-            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n, ts, (int)blockDim.x);
+            double cos_raw = 0.0;
+            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, ts, (int)blockDim.x);
             if (level == 0 && hit_ids_out) hit_ids_out[opix] = ent;
             if (ent < 0) {
                 val = mapped_color<D>(sv, sv.background, d);
             } else {
                 ShadeOut<D> so;
-                shade_hit<D>(sv, fp.time_millis, d, cur, ent, exiting, p, n, so);
+                shade_hit<D>(sv, fp.time_millis, d, cur, ent, exiting, cos_raw, p, n, so);
                 if (so.flags & NODE_UNDEFINED) {
                     val = Rgba{0.0, 0.0, 0.0, 0.0};
                     atomicAdd(ws.undefined_count, 1ull);

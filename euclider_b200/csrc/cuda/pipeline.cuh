@@ -40,6 +40,13 @@ __host__ __device__ inline int frame_row_of_local(const ChunkParams& c, int loca
     return (k * c.band_world + c.band_rank) * c.band_rows + local_row % c.band_rows;
 }
 
+// What the intersect kernel reports besides the hit point and normal.
+struct __align__(16) HitInfo {
+    int32_t entity;  // hit entity or -1
+    int32_t exiting; // angle_between(direction, normal) < pi/2 (mod.rs:117)
+    double cos_raw;  // dot(d, n) / (|d| |n|) for the intersector's normal: shading derives its angles from it
+};
+
 // Ray-tree node record written by the shade kernel and consumed by the bottom-up resolve.
 struct NodeMeta {
     double ratio;    // clamped reflection ratio
@@ -64,7 +71,7 @@ struct Workspace {
     double2* ray_od;    // D planes of `capacity`: plane k = components (2k, 2k+1) of [origin, direction]
     int32_t* ray_cur;   // entity the ray travels in; -1 = no ray (checkerboard pixel)
     double2* hit_pn;    // D planes: [location, raw normal]
-    int2* hit_ei;       // (hit entity or -1, exiting)
+    HitInfo* hit_ei;    // hit entity or -1, exiting, cos(direction, raw normal): one 128-bit access
     NodeMeta* meta;
     double2* res_rg;    // resolved colour, (r, g)
     double2* res_ba;    // (b, a)

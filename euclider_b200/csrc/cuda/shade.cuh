@@ -421,13 +421,18 @@ __device__ __noinline__ Vec<D> general_rotation(const Vec<D>& self_, const Vec<D
     return out;
 }
 
+// The angles every provider derives from the same two vectors.  The intersect kernel already
+// evaluated c = dot(d, n) / (|d| |n|) for the raw normal; negating a vector negates the dot product
+// and the quotient exactly, so cos(d, -n) = -c bit for bit and nothing is recomputed here.
+//   cos_raw    : direction vs the intersector's normal          (illumination_directional)
+//   cos_closer : direction vs normal_closer                     (illumination_global)
+//   from_theta : angle_between(direction, -normal_closer)       (Fresnel, Snell)
+
 // reflection_ratio_uniform / reflection_ratio_fresnel (surface.rs:201-244), before clamping
 template <int D>
-__device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& normal_closer,
-                                                   bool exiting) {
+__device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, double from_theta, bool exiting) {
+    // from_theta = angle_between(direction, -normal_closer), computed once per hit (ShadeAngles)
     if (sf.ratio_op == EUCL_RATIO_UNIFORM) return exiting ? 0.0 : sf.ratio_a;
-    const Vec<D> normal = -normal_closer;
-    const double from_theta = angle_between(dir, normal);
     const double from_index = exiting ? sf.ratio_a : sf.ratio_b;
     const double to_index = exiting ? sf.ratio_b : sf.ratio_a;
     const double to_theta = dm_asin((from_index / to_index) * dm_sin(from_theta));
@@ -449,10 +454,9 @@ __device__ __forceinline__ Vec<D> reflection_direction(const Vec<D>& dir, const 
 // threshold_direction_identity / threshold_direction_snell (surface.rs:259-288)
 template <int D>
 __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& normal_closer,
-                                                      bool exiting) {
+                                                      bool exiting, double from_theta) {
     if (sf.thr_op == EUCL_THR_IDENTITY) return dir;
     const Vec<D> normal = -normal_closer;
-    const double from_theta = angle_between(dir, normal);
     const double modifier = exiting ? sf.thr_a : 1.0 / sf.thr_a;
     const double to_theta = dm_asin(modifier * dm_sin(from_theta));
     const double angle_delta = to_theta - from_theta;
@@ -462,7 +466,7 @@ __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, con
 // The surface colour program (postfix) of surface `sf` at a hit.
 template <int D>
 __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& location,
-                                     const Vec<D>& normal_raw, const Vec<D>& normal_closer, double time_millis) {
+                                     const Vec<D>& normal_raw, double cos_raw, double cos_closer, double time_millis) {
     Rgba stack[8];
     int sp = 0;
     for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
@@ -472,7 +476,8 @@ __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurfac
             stack[sp++] = Rgba{op.f[0], op.f[1], op.f[2], op.f[3]};
         } else if (code == EUCL_COL_ILLUM_GLOBAL) { // surface.rs:410-422
             const Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
-            const double original_angle = angle_between(normal_closer, dir);
+            // angle_between(normal_closer, direction): same products and norms as (direction, normal_closer)
+            const double original_angle = angle_from_cos(cos_closer);
             const double angle = kPi - original_angle;
             const double ratio = angle / kFracPi2;
             stack[sp++] = combine_palette_color(dark, light, ratio);
@@ -482,7 +487,7 @@ __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurfac
 #pragma unroll
             for (int k = 0; k < D; ++k) light_direction[k] = op.f[8 + k];
             Vec<D> normal = normal_raw;
-            if (angle_between(dir, normal) > kFracPi2) normal = -normal;
+            if (angle_from_cos(cos_raw) > kFracPi2) normal = -normal; // angle_between(direction, raw normal)
             const double angle = angle_between(normal, -light_direction);
             const double ratio = 1.0 - angle / kPi;
             stack[sp++] = combine_palette_color(dark, light, ratio);

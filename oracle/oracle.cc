@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -520,8 +521,23 @@ struct Tracer {
         std::vector<NodeState> st;
         bool runaway = false;
 
-        Streams(const Tracer& t, int first, int root, const Vec<D>& loc, const Vec<D>& dir)
-            : tr(t), node_first(first), location(loc), direction(dir), st((size_t)(root - first + 1)) {}
+        explicit Streams(const Tracer& t) : tr(t), node_first(0) {}
+        // one Streams object is reused for every intersect call of a thread (only its storage: the
+        // lazily filled caches are reset), so the oracle does not spend its time in malloc
+        void reset(int first, int root, const Vec<D>& loc, const Vec<D>& dir) {
+            node_first = first;
+            location = loc;
+            direction = dir;
+            runaway = false;
+            const size_t n = (size_t)(root - first + 1);
+            if (st.size() < n) st.resize(n);
+            for (size_t k = 0; k < n; ++k) {
+                st[k].items.clear();
+                st[k].index_a = st[k].index_b = 0;
+                st[k].leaf_count = -1;
+                st[k].leaf_next = 0;
+            }
+        }
 
         // Provider::get (util.rs:395-419)
         Opt get(int n, int index) {
@@ -659,6 +675,8 @@ struct Tracer {
         }
     };
 
+    std::unique_ptr<Streams> scratch;
+
     // Universe::intersect + `provider.iter().next()` (mod.rs:61-83,110-112): first item only
     bool first_intersection(const EuclEntity& e, const Vec<D>& location, const Vec<D>& direction, Hit<D>* out) {
         if (e.node_first == e.node_root) { // plain primitive: no stream machinery needed
@@ -668,7 +686,9 @@ struct Tracer {
             *out = hits[0];
             return true;
         }
-        Streams streams(*this, e.node_first, e.node_root, location, direction);
+        if (!scratch) scratch.reset(new Streams(*this));
+        Streams& streams = *scratch;
+        streams.reset(e.node_first, e.node_root, location, direction);
         auto item = streams.get(e.node_root, 0);
         if (streams.runaway) counters.csg_runaway++;
         if (!item.some) return false;
@@ -679,7 +699,8 @@ struct Tracer {
     // all items of an entity's stream up to the first None (test hook)
     int all_intersections(const EuclEntity& e, const Vec<D>& location, const Vec<D>& direction, int max_items,
                           Hit<D>* out) {
-        Streams streams(*this, e.node_first, e.node_root, location, direction);
+        Streams streams(*this);
+        streams.reset(e.node_first, e.node_root, location, direction);
         int n = 0;
         while (n < max_items) {
             auto item = streams.get(e.node_root, n);
@@ -1125,17 +1146,22 @@ template <int D>
 int render_impl(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t width, uint32_t height, double time,
                 uint32_t row_begin, uint32_t row_end, int threads, uint8_t* out_rgb, int32_t* out_hit, uint64_t* stats) {
     if (threads < 1) threads = 1;
-    std::atomic<uint32_t> next_row{row_begin};
+    // dynamic scheduling over tiles of 128 pixels (the reference hands out one job per pixel,
+    // mod.rs:316-318; tiles keep every host thread busy even for a few sampled rows)
+    const uint64_t total = (uint64_t)(row_end - row_begin) * width;
+    const uint64_t tile = 128;
+    std::atomic<uint64_t> next_tile{0};
     std::vector<Tracer<D>> tracers;
     tracers.reserve((size_t)threads);
     for (int t = 0; t < threads; ++t) tracers.emplace_back(*scene, *camera, time);
     auto work = [&](int t) {
         Tracer<D>& tr = tracers[(size_t)t];
         for (;;) {
-            uint32_t y = next_row.fetch_add(1);
-            if (y >= row_end) break;
-            for (uint32_t x = 0; x < width; ++x) {
-                size_t idx = (size_t)(y - row_begin) * width + x;
+            const uint64_t begin = next_tile.fetch_add(tile);
+            if (begin >= total) break;
+            const uint64_t end = begin + tile < total ? begin + tile : total;
+            for (uint64_t idx = begin; idx < end; ++idx) {
+                const uint32_t y = row_begin + (uint32_t)(idx / width), x = (uint32_t)(idx % width);
                 tr.pixel((int)x, (int)y, (int)width, (int)height, out_rgb + 3 * idx, out_hit ? out_hit + idx : nullptr);
             }
         }
