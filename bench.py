@@ -321,6 +321,12 @@ def main():
         seg_per_frame = segs / args.steps / world if world > 1 else segs / args.steps
         roofline = {"bound": "fp64_issue", "unit": "Tflop/s", "peak": peak, "peak_source": "measured live (DADD/DMUL microbenchmark)",
                     "peak_dfma_tops": dfma.value, "traffic": None, "flops_per_segment": f_scene}
+        if args.scene == "3d_room" and (width, height) == (3840, 2160):
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_intersect launch (level 0 of a 4 Mi-pixel chunk,
+            # 4.19 M rays) from the committed ncu --set full capture (profiles/README.md); algorithmic bytes of that
+            # launch: none beyond its 212 B/node queue records (the frame itself is 3 B/pixel, written by k_final)
+            roofline["traffic"] = 219.868928e6 + 264.643072e6
+            roofline["traffic_note"] = "one level-0 k_intersect launch, 4.19 M rays, ncu capture of round 1"
         if prof is not None and prof["ms_intersect"] > 0:
             achieved = prof["segments"] * f_scene / (prof["ms_intersect"] * 1e-3) / 1e12
             roofline.update({"kernel": "k_intersect (all levels of one frame)", "achieved": achieved, "frac": achieved / peak,

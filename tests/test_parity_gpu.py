@@ -131,6 +131,24 @@ def test_full_size_rows_match_the_oracle(built_lib, oracle):
     assert np.array_equal(mega.data, img.data) and mega.stats["level_counts"] == img.stats["level_counts"]
 
 
+@pytest.mark.parametrize("name,size,depth", [("3d_fresnel", (1920, 1080), 10), ("3d_hallways", (3840, 2160), 10),
+                                             ("4d_frame", (3840, 2160), 10), ("4d_cylinders", (3840, 2160), 10),
+                                             ("4d_room", (7680, 4320), 10), ("4d_room", (7680, 4320), 16)])
+def test_baseline_configs_at_full_size(built_lib, oracle, name, size, depth):
+    """Every BASELINE.json config at its full resolution: sampled rows against the oracle (bit-exact),
+    idempotence, and the segment count of the sampled rows."""
+    env = load(name)
+    env.camera.max_depth = depth
+    w, h = size
+    img = env.render((w, h), want_hit_ids=True)
+    for r0 in (0, h // 3, h // 2 - 1, h // 2, h - 1):
+        rgb, hit, _ = oracle.render(env, w, h, rows=(r0, r0 + 1))
+        assert np.array_equal(img.data[r0:r0 + 1], rgb) and np.array_equal(img.hit_ids[r0:r0 + 1], hit)
+    assert img.stats["pixels"] == w * h and img.stats["level_counts"][0] == w * h
+    again = env.render((w, h))
+    assert np.array_equal(again.data, img.data)
+
+
 def test_device_buffer_entry_point(built_lib):
     import torch
 
