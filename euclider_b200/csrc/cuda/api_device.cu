@@ -252,6 +252,35 @@ struct MacroBuilder {
                 if (p.s1 * p.v0[axis] > 0) lo[axis] = std::max(lo[axis], edge);
                 else hi[axis] = std::min(hi[axis], edge);
             }
+            // a cylinder capped by two half-spaces whose normals are parallel to its axis
+            // (Cylinder::new_with_height, shape.rs:906-927): sphere around the finite cylinder
+            for (int i = 0; i < count; ++i) {
+                const EuclPrim& cy = f.prims[nd.a + i];
+                if (cy.kind != EUCL_PRIM_CYLINDER || !std::isfinite(cy.s0)) continue;
+                double s_lo = -INFINITY, s_hi = INFINITY;
+                for (int j = 0; j < count; ++j) {
+                    const EuclPrim& hs = f.prims[nd.a + j];
+                    if (hs.kind != EUCL_PRIM_HALFSPACE || !(hs.s1 == 1.0 || hs.s1 == -1.0)) continue;
+                    double nu = 0, nn = 0, uu = 0, nc = 0;
+                    for (int k = 0; k < D; ++k) {
+                        nu += hs.v0[k] * cy.v1[k];
+                        nn += hs.v0[k] * hs.v0[k];
+                        uu += cy.v1[k] * cy.v1[k];
+                        nc += hs.v0[k] * cy.v0[k];
+                    }
+                    if (!(nu * nu >= (1.0 - 1e-12) * nn * uu) || nu == 0.0) continue; // not parallel to the axis
+                    const double s = -(nc + hs.s0) / nu; // axis coordinate of the cap plane
+                    if (hs.s1 * nu > 0) s_lo = std::max(s_lo, s);
+                    else s_hi = std::min(s_hi, s);
+                }
+                if (std::isfinite(s_lo) && std::isfinite(s_hi) && s_lo <= s_hi) {
+                    Bound b{};
+                    const double mid = 0.5 * (s_lo + s_hi), half = 0.5 * (s_hi - s_lo);
+                    for (int k = 0; k < D; ++k) b.c[k] = cy.v0[k] + cy.v1[k] * mid;
+                    b.r2 = cy.s0 * cy.s0 + half * half;
+                    best = smaller(best, b);
+                }
+            }
             bool boxed = true;
             for (int k = 0; k < D; ++k) boxed = boxed && std::isfinite(lo[k]) && std::isfinite(hi[k]) && lo[k] <= hi[k];
             if (boxed) {
@@ -609,7 +638,7 @@ Workspace carve(EuclScene* s, int dim, int cap) {
     ws.bin_count = small + SmallLayout::bins;
     ws.order = (int32_t*)s->order.ptr;
     const bool bin = s->order.ptr != nullptr;
-    ws.n_bins = bin ? s->n_entities + 1 : 1;
+    ws.n_bins = bin ? 2 * s->n_entities + 1 : 1;
     return ws;
 }
 
@@ -653,8 +682,8 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     EUCL_CUDA(s->nodes.ensure(arena_bytes(dim, (size_t)want)));
                     s->arena_capacity = (int)want;
                     // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
-                    if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1))
-                        EUCL_CUDA(s->order.ensure(sizeof(int32_t) * (size_t)(s->n_entities + 1) * (size_t)want));
+                    if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && 2 * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1))
+                        EUCL_CUDA(s->order.ensure(sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * (size_t)want));
                 }
                 Workspace ws = carve(s, dim, s->arena_capacity);
                 EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));

@@ -137,8 +137,9 @@ __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_milli
     const double cos_closer = exiting ? -cos_raw : cos_raw;
     const bool needs_theta = sf.ratio_op == EUCL_RATIO_FRESNEL || sf.thr_op == EUCL_THR_SNELL;
     const double from_theta = needs_theta ? angle_from_cos(-cos_closer) : 0.0;
+    RefractionCache rc{needs_theta ? dm_sin(from_theta) : 0.0, 0.0, 0.0, false};
     // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
-    const double ratio = fmax(fmin(reflection_ratio<D>(sf, from_theta, exiting), 1.0), 0.0);
+    const double ratio = fmax(fmin(reflection_ratio<D>(sf, from_theta, exiting, rc), 1.0), 0.0);
     out.ratio = ratio;
     out.q = 0u;
     out.flags = 0u;
@@ -154,7 +155,7 @@ __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_milli
             out.flags |= NODE_HAS_SC;
             have_t = true;
         } else {
-            Vec<D> td = threshold_direction<D>(sf, dir, n_closer, exiting, from_theta);
+            Vec<D> td = threshold_direction<D>(sf, dir, n_closer, exiting, from_theta, rc);
             const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
             const int dest = exiting ? material_at<D>(sv, new_origin) : ent;
             if (dest >= 0) {
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
         const int node = off + i;
         const bool valid = i < cnt && ws.ray_cur[node] >= 0;
         int ent = -1;
+        bool exiting_flag = false;
         if (valid) {
             Vec<D> o, d, p, n;
             load_ray<D>(ws, node, o, d);
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
             double cos_raw = 0.0;
             ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, ts, (int)blockDim.x);
             ws.hit_ei[node] = HitInfo{ent, exiting ? 1 : 0, cos_raw};
+            exiting_flag = exiting;
             if (ent >= 0) store_hit<D>(ws, node, p, n);
         }
         if (ws.n_bins > 1) {
@@ -288,7 +291,8 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
             // one atomicAdd per (warp, distinct key), ranks from the match mask
             const unsigned active = __ballot_sync(0xffffffffu, valid);
             if (valid) {
-                const int key = ent + 1;
+                // key: miss = 0, else 1 + 2 * entity + exiting (exiting hits run material_at, entering ones do not)
+                const int key = ent < 0 ? 0 : 1 + 2 * ent + (exiting_flag ? 1 : 0);
                 const unsigned peers = __match_any_sync(active, key);
                 const int leader = __ffs(peers) - 1;
                 int slot = 0;

@@ -429,13 +429,32 @@ __device__ __noinline__ Vec<D> general_rotation(const Vec<D>& self_, const Vec<D
 //   from_theta : angle_between(direction, -normal_closer)       (Fresnel, Snell)
 
 // reflection_ratio_uniform / reflection_ratio_fresnel (surface.rs:201-244), before clamping
+// Values Fresnel and Snell both derive from from_theta; computed at most once per hit.  The two
+// providers take asin of (from_index / to_index) * sin and of modifier * sin: for a consistent glass
+// description these arguments are the SAME double (e.g. 1.458 / 1 and 1.458), detected by comparing
+// the bits of the arguments, never assumed.
+struct RefractionCache {
+    double sin_from;   // sin(from_theta)
+    double asin_arg;   // argument of the cached asin
+    double asin_value; // asin(asin_arg)
+    bool have_asin;
+};
+__device__ __forceinline__ double cached_asin(RefractionCache& rc, double arg) {
+    if (rc.have_asin && __double_as_longlong(arg) == __double_as_longlong(rc.asin_arg)) return rc.asin_value;
+    rc.asin_arg = arg;
+    rc.asin_value = dm_asin(arg);
+    rc.have_asin = true;
+    return rc.asin_value;
+}
+
 template <int D>
-__device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, double from_theta, bool exiting) {
-    // from_theta = angle_between(direction, -normal_closer), computed once per hit (ShadeAngles)
+__device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, double from_theta, bool exiting,
+                                                   RefractionCache& rc) {
+    // from_theta = angle_between(direction, -normal_closer), computed once per hit
     if (sf.ratio_op == EUCL_RATIO_UNIFORM) return exiting ? 0.0 : sf.ratio_a;
     const double from_index = exiting ? sf.ratio_a : sf.ratio_b;
     const double to_index = exiting ? sf.ratio_b : sf.ratio_a;
-    const double to_theta = dm_asin((from_index / to_index) * dm_sin(from_theta));
+    const double to_theta = cached_asin(rc, (from_index / to_index) * rc.sin_from);
     if (isnan(to_theta)) return 1.0;
     const double cf = dm_cos(from_theta), ct = dm_cos(to_theta);
     const double p1s = from_index * cf, p2s = to_index * ct;
@@ -454,11 +473,11 @@ __device__ __forceinline__ Vec<D> reflection_direction(const Vec<D>& dir, const 
 // threshold_direction_identity / threshold_direction_snell (surface.rs:259-288)
 template <int D>
 __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& normal_closer,
-                                                      bool exiting, double from_theta) {
+                                                      bool exiting, double from_theta, RefractionCache& rc) {
     if (sf.thr_op == EUCL_THR_IDENTITY) return dir;
     const Vec<D> normal = -normal_closer;
     const double modifier = exiting ? sf.thr_a : 1.0 / sf.thr_a;
-    const double to_theta = dm_asin(modifier * dm_sin(from_theta));
+    const double to_theta = cached_asin(rc, modifier * rc.sin_from);
     const double angle_delta = to_theta - from_theta;
     return general_rotation<D>(normal, dir, angle_delta, dir);
 }
