@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--band-rows", type=int, default=16)
     ap.add_argument("--ref-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: ranks store their rows into GPU 0's frame through CUDA IPC (peer) or NCCL gather")
+    ap.add_argument("--check", action="store_true", help="N > 1: compare the gathered frame with a single-GPU render")
     args = ap.parse_args()
     width, height = DEFAULT_CONFIGS.get(args.scene, (3840, 2160))
     width, height = args.width or width, args.height or height
@@ -186,6 +189,7 @@ def main():
     import torch.distributed as dist
 
     import euclider_b200 as eb
+    from euclider_b200 import bands
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,30 +212,66 @@ def main():
     band_rows = args.band_rows if world > 1 else 0
     opts = eb.EuclRenderOpts(width=width, height=height, band_rows=band_rows, band_rank=rank, band_world=world)
     my_rows = int(eb.lib().eucl_band_rows_for_rank(opts)) if world > 1 else height
-    d_rows = torch.empty((max(my_rows, 1), width, 3), dtype=torch.uint8, device=device)
-    frame = torch.empty((height, width, 3), dtype=torch.uint8, device=device) if rank == 0 else None
-    # gather plan: every rank sends its compact rows; rank 0 scatters them to frame rows
-    rows_of = []
-    if world > 1:
+    frame_bytes = height * width * 3
+    peer = world > 1 and args.gather == "peer"
+    frame_ptr, frame = 0, None
+    if world == 1:
+        frame = torch.empty((height, width, 3), dtype=torch.uint8, device=device)
+        frame_ptr = frame.data_ptr()
+    elif peer:
+        # One frame buffer on GPU 0, mapped into every rank through CUDA IPC: each rank's pack kernel
+        # stores its rows straight into it over NVLink, so the gather IS the last kernel of the frame.
+        import ctypes as C
+
+        handle = torch.zeros(eb._capi.EUCL_IPC_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        ptr = C.c_void_p()
+        if rank == 0:
+            eb._capi.check(eb.lib().eucl_device_malloc(local_rank, frame_bytes, C.byref(ptr)))
+            buf = (C.c_uint8 * eb._capi.EUCL_IPC_HANDLE_BYTES)()
+            eb._capi.check(eb.lib().eucl_ipc_export(ptr, buf))
+            handle.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            buf = (C.c_uint8 * eb._capi.EUCL_IPC_HANDLE_BYTES)(*handle.cpu().tolist())
+            eb._capi.check(eb.lib().eucl_ipc_open(buf, local_rank, C.byref(ptr)))
+        frame_ptr = ptr.value
+        if rank == 0:  # torch view of the raw allocation (for the copy to the host)
+            class _Raw:
+                __cuda_array_interface__ = {"shape": (height, width, 3), "typestr": "|u1", "data": (frame_ptr, False),
+                                            "version": 2}
+            frame = torch.as_tensor(_Raw(), device=device)
+    else:
+        # NCCL gather of compact row blocks, scattered to frame rows on rank 0
+        d_rows = torch.empty((max(my_rows, 1), width, 3), dtype=torch.uint8, device=device)
+        frame = torch.empty((height, width, 3), dtype=torch.uint8, device=device) if rank == 0 else None
+        rows_of = []
         for r in range(world):
-            o = eb.EuclRenderOpts(width=width, height=height, band_rows=band_rows, band_rank=r, band_world=world)
-            n_local = int(eb.lib().eucl_band_rows_for_rank(o))
-            idx = [((k // band_rows) * world + r) * band_rows + k % band_rows for k in range(n_local)]
+            idx = bands.local_rows(height, band_rows, r, world)
             rows_of.append(torch.tensor(idx, dtype=torch.long, device=device))
         max_rows = max(len(x) for x in rows_of)
         send = torch.zeros((max_rows, width, 3), dtype=torch.uint8, device=device)
         recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    host = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
 
     def step(profile=False):
+        if world == 1 or peer:
+            st = env.render_device(frame_ptr, (width, height), args.time, device=local_rank, band_rows=band_rows,
+                                   band_rank=rank, band_world=world, compact_rows=False, profile=profile)
+            if peer:
+                dist.barrier()  # every rank's rows have landed in GPU 0's frame (render_device is synchronous)
+            return st
         st = env.render_device(d_rows.data_ptr(), (width, height), args.time, device=local_rank, band_rows=band_rows,
-                               band_rank=rank, band_world=world, compact_rows=world > 1, profile=profile)
-        if world > 1:
-            send[:my_rows].copy_(d_rows[:my_rows])
-            dist.gather(send, recv, dst=0)
-            if rank == 0:
-                for r in range(world):
-                    frame.index_copy_(0, rows_of[r], recv[r][:len(rows_of[r])])
+                               band_rank=rank, band_world=world, compact_rows=True, profile=profile)
+        send[:my_rows].copy_(d_rows[:my_rows])
+        dist.gather(send, recv, dst=0)
+        if rank == 0:
+            for r in range(world):
+                frame.index_copy_(0, rows_of[r], recv[r][:len(rows_of[r])])
         return st
+
+    def frame_to_host():
+        """rank 0: device frame -> pinned host buffer (the e2e leg)."""
+        host.copy_(frame, non_blocking=False)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -271,7 +311,6 @@ def main():
         # profile pass: per-kernel-family device times (extra events; not part of the timed region)
         prof = step(profile=True)
         # end-to-end through the reference-facing call with a pinned HOST frame buffer
-        host = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory()
         host_np = host.numpy()
         for _ in range(3):
             env.render((width, height), args.time, device=local_rank, out=host_np)
@@ -287,9 +326,7 @@ def main():
                "h2d_bytes_per_step": 256, "d2h_bytes_per_step": width * height * 3}
     elif rank == 0:
         prof = None
-        # N > 1: the gather already lands the frame on GPU 0; e2e adds its copy to pinned host memory
-        host = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory()
-        e2e = None
+        e2e = None  # N > 1: measured below (bands -> GPU 0 -> pinned host)
     if world > 1:
         # e2e at N GPUs: bands -> gather -> host copy on rank 0, timed by wall clock between barriers
         sync_all()
@@ -299,7 +336,7 @@ def main():
             st = step()
             e2e_segs += st["segments"]
             if rank == 0:
-                host.copy_(frame, non_blocking=False)
+                frame_to_host()
         sync_all()
         e2e_s = time.perf_counter() - t0
         tt = torch.tensor([e2e_s, float(e2e_segs)], dtype=torch.float64, device=device)
@@ -349,12 +386,23 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.scene} {width}x{height} max_depth {env.camera.max_depth} time {args.time}",
                        "pipeline": args.pipeline, "segments_per_frame": seg_per_frame * (world if world > 1 else 1),
-                       "parallelism": f"row bands of {band_rows} x {world} ranks, gather to rank 0" if world > 1 else "single GPU",
+                       "parallelism": (f"row bands of {band_rows} x {world} ranks, "
+                                       + ("peer stores into GPU 0's frame (CUDA IPC over NVLink)" if peer else "NCCL gather to rank 0"))
+                       if world > 1 else "single GPU",
                        "l2": "node arena (GBs per chunk) is far larger than the 126 MB L2; no explicit flush"},
             "fps": 1e3 / ms_per_step, "e2e": e2e, "gpu_launches": launches, "retries": retries, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
+    if world > 1 and args.check:
+        step()
+        sync_all()
+        if rank == 0:
+            frame_to_host()
+            env.set_stream(0, device=local_rank)
+            whole = env.render((width, height), args.time, device=local_rank)
+            same = bool(np.array_equal(whole.data, host.numpy()))
+            print(json.dumps({"check": "gathered frame == single-GPU frame", "equal": same}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

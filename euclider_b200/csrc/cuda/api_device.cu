@@ -825,6 +825,21 @@ int eucl_scene_set_stream(EuclScene* s, void* cuda_stream) {
     return EUCL_OK;
 }
 
+int eucl_device_malloc(int device, uint64_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes == 0) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_device_malloc: bad argument");
+    if (eucl_device_count() <= 0) return fail(EUCL_ERR_NO_DEVICE, "no CUDA device available");
+    EUCL_CUDA(cudaSetDevice(device));
+    EUCL_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+    return EUCL_OK;
+}
+
+int eucl_device_free(int device, void* d_ptr) {
+    if (!d_ptr) return EUCL_OK;
+    EUCL_CUDA(cudaSetDevice(device));
+    EUCL_CUDA(cudaFree(d_ptr));
+    return EUCL_OK;
+}
+
 int eucl_ipc_export(void* d_ptr, uint8_t handle[EUCL_IPC_HANDLE_BYTES]) {
     static_assert(sizeof(cudaIpcMemHandle_t) <= EUCL_IPC_HANDLE_BYTES, "IPC handle size");
     if (!d_ptr || !handle) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_ipc_export: null argument");

@@ -94,7 +94,10 @@ struct Launch {
     int grid_max; // upper bound on blocks for queue kernels
 };
 
-constexpr int kBlock = 128;
+#ifndef EUCL_BLOCK
+#define EUCL_BLOCK 128
+#endif
+constexpr int kBlock = EUCL_BLOCK;
 constexpr int kMaxBins = 64; // shade-coherence bins (miss, then 2 per entity: entering / exiting); larger scenes shade unbinned
 
 // kernels.cu

@@ -307,6 +307,12 @@ int eucl_render(EuclScene* scene, const EuclCamera* camera, const EuclRenderOpts
 int eucl_render_device(EuclScene* scene, const EuclCamera* camera, const EuclRenderOpts* opts,
                        void* d_out_rgb8, void* d_out_hit_ids, EuclStats* stats);
 
+/* Plain device allocations (cudaMalloc / cudaFree) for buffers that are shared through eucl_ipc_*:
+ * an IPC handle must name the base of its own allocation, which framework allocators that carve
+ * tensors out of large pools cannot guarantee. */
+int eucl_device_malloc(int device, uint64_t bytes, void** d_ptr);
+int eucl_device_free(int device, void* d_ptr);
+
 /* Cross-process frame buffer sharing for the multi-GPU gather (one process per GPU):
  * rank 0 exports its device frame buffer, the other ranks map it and render straight into it. */
 #define EUCL_IPC_HANDLE_BYTES 64
