@@ -143,6 +143,7 @@ PROTOTYPES = {
     "eucl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eucl_ipc_open": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "eucl_ipc_close": (C.c_int, [C.c_void_p]),
+    "eucl_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "eucl_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

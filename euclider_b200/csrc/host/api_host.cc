@@ -1,4 +1,5 @@
 // C-ABI entry points of the scene front end (host only).  See include/euclider_b200.h.
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -71,6 +72,18 @@ const EuclFlatScene* eucl_parsed_flat(EuclParsedScene* p) {
 }
 
 void eucl_parsed_destroy(EuclParsedScene* p) { delete p; }
+
+int eucl_write_ppm(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb) {
+    if (!path || !rgb || width == 0 || height == 0) return eucl::fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_write_ppm: bad argument");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return eucl::fail(EUCL_ERR_INVALID_ARGUMENT, std::string("eucl_write_ppm: cannot open ") + path);
+    std::fprintf(f, "P6\n%u %u\n255\n", width, height);
+    bool ok = true;
+    for (uint32_t y = 0; y < height && ok; ++y) // row 0 of the buffer is the BOTTOM of the picture
+        ok = std::fwrite(rgb + (size_t)(height - 1 - y) * width * 3, 1, (size_t)width * 3, f) == (size_t)width * 3;
+    ok = std::fclose(f) == 0 && ok;
+    return ok ? EUCL_OK : eucl::fail(EUCL_ERR_INVALID_ARGUMENT, std::string("eucl_write_ppm: short write to ") + path);
+}
 
 uint32_t eucl_band_rows_for_rank(const EuclRenderOpts* o) {
     if (!o || o->height == 0) return 0;

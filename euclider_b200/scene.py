@@ -47,6 +47,16 @@ class RawImage2d:
     def to_top_down(self) -> np.ndarray:
         return self.data[::-1]
 
+    def save(self, path: Union[str, os.PathLike]) -> None:
+        """Writes the frame top-down: `.ppm` through the library (eucl_write_ppm), anything else via Pillow."""
+        path = str(path)
+        if path.lower().endswith(".ppm"):
+            check(lib().eucl_write_ppm(path.encode(), self.width, self.height, np.ascontiguousarray(self.data).ctypes.data))
+        else:
+            from PIL import Image
+
+            Image.fromarray(np.ascontiguousarray(self.to_top_down())).save(path)
+
 
 def _decode_image(path: Path) -> Tuple[int, int, bytes]:
     """Decodes to RGBA8, row 0 = top -- the layout `image::DynamicImage::get_pixel` exposes

@@ -320,6 +320,11 @@ int eucl_ipc_export(void* d_ptr, uint8_t handle[EUCL_IPC_HANDLE_BYTES]);
 int eucl_ipc_open(const uint8_t handle[EUCL_IPC_HANDLE_BYTES], int device, void** d_ptr);
 int eucl_ipc_close(void* d_ptr);
 
+/* Presentation helper (the step AFTER the hot path; the reference uploads the buffer as a GL texture
+ * and blits it, src/simulation.rs:88-96): writes a binary PPM (P6), flipping the bottom-up rows of
+ * Environment::render to the top-down order image files use. */
+int eucl_write_ppm(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8_bottom_up);
+
 /* FP64 issue-rate microbenchmark (DADD/DMUL/DFMA), the roofline denominator of this path.
  * Returns measured T op/s (one op = one double instruction per lane). */
 int eucl_fp64_peak(int device, double* dadd_tops, double* dmul_tops, double* dfma_tops);

@@ -64,3 +64,15 @@ MINIMAL_SCENE = """
   "background": {"MappedTextureImpl3::new": [{"uv_sphere_3": [{"Point3::new": [0, 0, 0]}]},
                                               {"texture_image_linear": ["./none.png"]}]}}}
 """
+
+
+def test_write_ppm_flips_rows(built_lib, tmp_path):
+    import numpy as np
+
+    rgb = np.arange(2 * 3 * 3, dtype=np.uint8).reshape(3, 2, 3)  # 3 rows (bottom-up) of 2 pixels
+    path = tmp_path / "t.ppm"
+    assert built_lib.eucl_write_ppm(str(path).encode(), 2, 3, rgb.ctypes.data) == 0
+    data = path.read_bytes()
+    assert data.startswith(b"P6\n2 3\n255\n")
+    assert data[len(b"P6\n2 3\n255\n"):] == rgb[::-1].tobytes()
+    assert built_lib.eucl_write_ppm(b"/nonexistent-dir/x.ppm", 2, 3, rgb.ctypes.data) == -1
