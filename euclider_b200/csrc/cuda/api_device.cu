@@ -663,6 +663,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         EUCL_CUDA(s->small.ensure(sizeof(int32_t) * kSmallInts));
         if (s->arena_factor <= 0.0) s->arena_factor = std::max(1.0, (double)env_int("EUCL_ARENA_FACTOR_X10", 45) / 10.0);
         Launch l{s->stream, s->d_blob, s->smem_bytes, s->sm_count * env_int("EUCL_BLOCKS_PER_SM", 8)};
+        const bool tree_resolve = env_int("EUCL_TREE_RESOLVE", 0) != 0; // 1: one pointer-chasing kernel instead of the level-by-level k_resolve launches (fewer launches, but 3x slower on glass scenes: measured)
 
         for (int row0 = 0; row0 < (int)my_rows; row0 += rows_per_chunk) {
             ChunkParams cp{};
@@ -718,10 +719,14 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     }
                     launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
                     mark(2);
-                    for (int level = (int)cam->max_depth - 1; level >= 1; --level) launch_resolve(dim, l, ws, level);
-                    launch_final(dim, l, fp, cp, ws, d_rgb);
+                    if (tree_resolve) {
+                        launch_final_tree(l, fp, cp, ws, d_rgb);
+                    } else {
+                        for (int level = (int)cam->max_depth - 1; level >= 1; --level) launch_resolve(dim, l, ws, level);
+                        launch_final(dim, l, fp, cp, ws, d_rgb);
+                    }
                     mark(3);
-                    st.launches += 3 + 2 * cam->max_depth + (cam->max_depth > 0 ? cam->max_depth - 1 : 0);
+                    st.launches += 3 + 2 * cam->max_depth + (tree_resolve || cam->max_depth == 0 ? 0 : cam->max_depth - 1);
                 }
                 EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
                                           s->stream));

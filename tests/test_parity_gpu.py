@@ -168,3 +168,12 @@ def test_errors_are_statuses_not_aborts(built_lib):
     with pytest.raises(eb.EuclError) as err:
         env.render((8, 8))
     assert err.value.status == -1
+
+
+def test_tree_resolve_variant_is_identical(built_lib, monkeypatch):
+    """EUCL_TREE_RESOLVE=1 resolves each pixel's ray tree in one kernel (k_final_tree) instead of level by level."""
+    env = load("3d_room")
+    a = env.render((160, 90), time=0.3)
+    monkeypatch.setenv("EUCL_TREE_RESOLVE", "1")
+    b = env.render((160, 90), time=0.3)
+    assert np.array_equal(a.data, b.data) and b.stats["launches"] < a.stats["launches"]
