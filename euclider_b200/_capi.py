@@ -138,6 +138,8 @@ PROTOTYPES = {
                               C.POINTER(EuclStats)]),
     "eucl_render_device": (C.c_int, [C.c_void_p, C.POINTER(EuclCamera), C.POINTER(EuclRenderOpts), C.c_void_p,
                                      C.c_void_p, C.POINTER(EuclStats)]),
+    "eucl_trace_path": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "eucl_device_malloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "eucl_device_free": (C.c_int, [C.c_int, C.c_void_p]),
     "eucl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -74,6 +74,7 @@ struct EuclScene {
     DeviceBuffer frame;    // device frame buffer for eucl_render (host output)
     DeviceBuffer hit_ids;  // device hit-id map for eucl_render
     DeviceBuffer order;    // per-bin node lists of the level being shaded
+    DeviceBuffer path_io;  // eucl_trace_path staging
     int n_entities = 0;
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
@@ -400,6 +401,7 @@ void eucl_scene_destroy(EuclScene* s) {
     s->frame.release();
     s->hit_ids.release();
     s->order.release();
+    s->path_io.release();
     if (s->h_small) cudaFreeHost(s->h_small);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -827,6 +829,39 @@ int eucl_scene_set_stream(EuclScene* s, void* cuda_stream) {
     EUCL_CUDA(cudaSetDevice(s->device));
     EUCL_CUDA(cudaStreamSynchronize(s->stream));
     s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+    return EUCL_OK;
+}
+
+int eucl_trace_path(EuclScene* s, const double* location, const double* direction, double distance, double* out_location,
+                    double* out_direction) {
+    if (!s || !location || !direction || !out_location || !out_direction)
+        return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_trace_path: null argument");
+    EUCL_CUDA(cudaSetDevice(s->device));
+    const int D = s->dim;
+    EUCL_CUDA(s->path_io.ensure(sizeof(double) * 4 * EUCL_MAX_DIM + 16));
+    double* d_in = (double*)s->path_io.ptr;
+    double* d_out = d_in + 2 * EUCL_MAX_DIM;
+    int* d_found = (int*)(d_out + 2 * EUCL_MAX_DIM);
+    double h_in[2 * EUCL_MAX_DIM] = {0};
+    for (int k = 0; k < D; ++k) {
+        h_in[k] = location[k];
+        h_in[D + k] = direction[k];
+    }
+    EUCL_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, s->stream));
+    Launch l{s->stream, s->d_blob, s->smem_bytes, 1};
+    launch_trace_path(D, l, d_in, distance, d_out, d_found);
+    double h_out[2 * EUCL_MAX_DIM];
+    int h_found = 0;
+    EUCL_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, s->stream));
+    EUCL_CUDA(cudaMemcpyAsync(&h_found, d_found, sizeof h_found, cudaMemcpyDeviceToHost, s->stream));
+    EUCL_CUDA(cudaStreamSynchronize(s->stream));
+    EUCL_CUDA(cudaGetLastError());
+    if (h_found < 0) return fail(EUCL_ERR_SCENE_LIMIT, "eucl_trace_path: more than 100000 surface crossings");
+    if (h_found == 0) return 1; /* the start point lies in no entity: Option::None in the reference */
+    for (int k = 0; k < D; ++k) {
+        out_location[k] = h_out[k];
+        out_direction[k] = h_out[D + k];
+    }
     return EUCL_OK;
 }
 

@@ -664,6 +664,67 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
     }
 }
 
+// Universe::trace_path_unknown / trace_path (mod.rs:186-227,273-286) with Surface::get_path
+// (surface.rs:164-197): moves a point `distance` along a direction through the universe, crossing
+// surfaces and applying the material transitions (a LinearSpace void stretches the step).  This is
+// what the reference's cameras call before every frame; one thread, the recursion unrolled into a
+// loop (the reference recurses once per crossed surface).
+// out: [0..D) location, [D..2D) direction, out_found: 1 ok, 0 start point in no entity, -1 step limit
+template <int D>
+__global__ void __launch_bounds__(32) k_trace_path(const uint8_t* __restrict__ blob, const double* __restrict__ in,
+                                                   double distance, double* __restrict__ out, int* __restrict__ out_found) {
+    const SceneView& sv = stage_scene(blob);
+    double* ts = plane_scratch(blob);
+    if (threadIdx.x != 0) return;
+    Vec<D> loc, dir;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        loc[k] = in[k];
+        dir[k] = in[D + k];
+    }
+    int belongs_to = material_at<D>(sv, loc);
+    if (belongs_to < 0) {
+        *out_found = 0;
+        return;
+    }
+    material_enter<D>(sv, belongs_to, dir);
+    int found = -1;
+    for (int step = 0; step < 100000; ++step) {
+        const ClosestHit h = closest_hit<D>(sv, loc, dir, ts, (int)blockDim.x);
+        bool moved = false;
+        if (h.entity >= 0 && !(distance - h.t <= 0.0)) { // get_path: Some
+            Vec<D> p, n_raw;
+            hit_geometry<D>(sv, h.prim, h.flags, loc, dir, h.t, p, n_raw);
+            const bool exiting = angle_from_cos(angle_cos(dir, n_raw)) < kFracPi2;
+            const Vec<D> n_closer = exiting ? -n_raw : n_raw;
+            const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
+            const int dest = exiting ? material_at<D>(sv, new_origin) : h.entity;
+            if (dest >= 0) {
+                Vec<D> nd = dir;
+                material_exit<D>(sv, belongs_to, nd);
+                material_enter<D>(sv, dest, nd);
+                distance = distance - h.t;
+                belongs_to = dest;
+                loc = new_origin;
+                dir = nd;
+                moved = true;
+            }
+        }
+        if (!moved) { // Material::trace_path (material.rs:54-56,144-146), then exit
+            loc = loc + dir * distance;
+            material_exit<D>(sv, belongs_to, dir);
+            found = 1;
+            break;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        out[k] = loc[k];
+        out[D + k] = dir[k];
+    }
+    *out_found = found;
+}
+
 // FP64 issue-rate microbenchmark: 8 independent dependency chains per thread
 template <int OP>
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double seed) {
@@ -742,6 +803,11 @@ void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const Ch
         (k_megakernel<4><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, out_rgb8, hit_ids_out)));
 }
 
+void launch_trace_path(int dim, const Launch& l, const double* d_in, double distance, double* d_out, int* d_found) {
+    EUCL_DISPATCH_DIM(dim, (k_trace_path<3><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, d_in, distance, d_out, d_found)),
+                      (k_trace_path<4><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, d_in, distance, d_out, d_found)));
+}
+
 cudaError_t configure_kernels(size_t smem_bytes) {
     if (smem_bytes <= 48 * 1024) return cudaSuccess;
     const int v = (int)smem_bytes;
@@ -758,6 +824,8 @@ cudaError_t configure_kernels(size_t smem_bytes) {
     EUCL_SET_SMEM(k_shade<4>);
     EUCL_SET_SMEM(k_megakernel<3>);
     EUCL_SET_SMEM(k_megakernel<4>);
+    EUCL_SET_SMEM(k_trace_path<3>);
+    EUCL_SET_SMEM(k_trace_path<4>);
 #undef EUCL_SET_SMEM
     return cudaSuccess;
 }

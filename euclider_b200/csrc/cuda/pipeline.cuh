@@ -113,6 +113,7 @@ void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkPa
 void launch_final_tree(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, uint8_t* out_rgb8);
 void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                        uint8_t* out_rgb8, int32_t* hit_ids_out);
+void launch_trace_path(int dim, const Launch& l, const double* d_in, double distance, double* d_out, int* d_found);
 cudaError_t configure_kernels(size_t smem_bytes);
 int fp64_peak(double* dadd, double* dmul, double* dfma); // T op/s on the current device
 

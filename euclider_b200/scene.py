@@ -130,6 +130,39 @@ class Environment:
                                        C.byref(stats)))
         return stats_to_dict(stats)
 
+    def trace_path_unknown(self, location: Sequence[float], direction: Sequence[float], distance: float, *,
+                           device: int = 0) -> Optional[Tuple[list, list]]:
+        """Universe::trace_path_unknown (src/universe/mod.rs:273-286): the point reached by travelling
+        `distance` along `direction` through the universe (voids stretch or shrink the step) and the
+        direction of travel there; None when `location` lies in no entity.  The reference's cameras
+        move with this call (d3/entity/camera.rs:223-243)."""
+        dim = self.dim
+        loc = (C.c_double * dim)(*[float(v) for v in location[:dim]])
+        dirv = (C.c_double * dim)(*[float(v) for v in direction[:dim]])
+        out_l, out_d = (C.c_double * dim)(), (C.c_double * dim)()
+        status = lib().eucl_trace_path(self._device_scene(device), loc, dirv, float(distance), out_l, out_d)
+        if status == 1:
+            return None
+        check(status)
+        return list(out_l), list(out_d)
+
+    def move_camera(self, direction: Sequence[float], distance: float, *, device: int = 0) -> bool:
+        """Translates `self.camera.location` like the translation part of the reference's camera
+        `update` (d3/entity/camera.rs:223-243): normalised direction, trace_path_unknown, new location.
+        (The reference additionally turns the view when the void bends the path; it labels that code
+        "not tested", and it is not reproduced here.)  Returns False when the camera is in no entity."""
+        dim = self.dim
+        norm = sum(float(v) * float(v) for v in direction[:dim]) ** 0.5
+        if norm == 0.0:
+            return True
+        unit = [float(v) / norm for v in direction[:dim]]
+        res = self.trace_path_unknown([self.camera.location[k] for k in range(dim)], unit, distance * norm, device=device)
+        if res is None:
+            return False
+        for k in range(dim):
+            self.camera.location[k] = res[0][k]
+        return True
+
     # -- plumbing ----------------------------------------------------------------------------------
     @property
     def flat(self) -> EuclFlatScene:

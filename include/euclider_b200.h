@@ -307,6 +307,16 @@ int eucl_render(EuclScene* scene, const EuclCamera* camera, const EuclRenderOpts
 int eucl_render_device(EuclScene* scene, const EuclCamera* camera, const EuclRenderOpts* opts,
                        void* d_out_rgb8, void* d_out_hit_ids, EuclStats* stats);
 
+/* Universe::trace_path_unknown (src/universe/mod.rs:273-286): moves `location` by `distance` along
+ * `direction` THROUGH the universe -- surfaces are crossed with the material transitions of the
+ * entities on either side, so a step through a LinearSpace void is stretched or shrunk.  The
+ * reference's cameras call this before every frame to translate themselves
+ * (d3/entity/camera.rs:223-243); here it lets a headless caller drive a camera path the same way.
+ * Returns 0 and the new location / direction, 1 if `location` lies in no entity (the reference's
+ * `None`), or a negative EuclStatus.  Arrays hold `dim` doubles. */
+int eucl_trace_path(EuclScene* scene, const double* location, const double* direction, double distance,
+                    double* out_location, double* out_direction);
+
 /* Plain device allocations (cudaMalloc / cudaFree) for buffers that are shared through eucl_ipc_*:
  * an IPC handle must name the base of its own allocation, which framework allocators that carve
  * tensors out of large pools cannot guarantee. */

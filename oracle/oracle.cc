@@ -1086,6 +1086,45 @@ struct Tracer {
         return mapped_color(s.background, direction); // `direction.to_point()`
     }
 
+    // Universe::trace_path (mod.rs:186-227) with Surface::get_path inlined (surface.rs:164-197)
+    void trace_path(double distance, int belongs_to, const Vec<D>& location, const Vec<D>& direction, int budget,
+                    Vec<D>* out_location, Vec<D>* out_direction, bool* runaway) {
+        Context c;
+        c.origin_entity = belongs_to;
+        if (budget > 0 && trace_closest(location, direction, &c)) {
+            if (!(distance - c.hit.distance <= 0.0)) {
+                double new_distance = distance - c.hit.distance;
+                Vec<D> new_origin = c.hit.location + (-c.normal_closer) * APPROX_EPSILON * 128.0;
+                int destination = c.exiting ? material_at(new_origin) : c.hit_entity;
+                if (destination >= 0) {
+                    Vec<D> transitioned = c.direction;
+                    material_exit(belongs_to, transitioned);
+                    material_enter(destination, transitioned);
+                    trace_path(new_distance, destination, new_origin, transitioned, budget - 1, out_location, out_direction,
+                               runaway);
+                    return;
+                }
+            }
+        }
+        if (budget <= 0) *runaway = true;
+        // Material::trace_path (material.rs:54-56,144-146) then exit
+        Vec<D> new_location = location + direction * distance;
+        Vec<D> new_direction = direction;
+        material_exit(belongs_to, new_direction);
+        *out_location = new_location;
+        *out_direction = new_direction;
+    }
+    // Universe::trace_path_unknown (mod.rs:273-286); false = None
+    bool trace_path_unknown(double distance, const Vec<D>& location, const Vec<D>& direction, Vec<D>* out_location,
+                            Vec<D>* out_direction, bool* runaway) {
+        int belongs_to = material_at(location);
+        if (belongs_to < 0) return false;
+        Vec<D> transitioned = direction;
+        material_enter(belongs_to, transitioned);
+        trace_path(distance, belongs_to, location, transitioned, 4000, out_location, out_direction, runaway);
+        return true;
+    }
+
     // camera (d3/entity/camera.rs:164-185,369-390; d4/entity/camera.rs:155-176)
     Vec<D> ray_vector(int x, int y, int width, int height) const {
         double rel_x = (double)(x - width / 2) + (double)(1 - width % 2) / 2.0;
@@ -1263,6 +1302,32 @@ int oracle_prim_inside(int dim, const EuclPrim* prim, const double* point) {
     if (dim == 2) return prim_inside<2>(*prim, load<2>(point));
     if (dim == 3) return prim_inside<3>(*prim, load<3>(point));
     return prim_inside<4>(*prim, load<4>(point));
+}
+
+// Universe::trace_path_unknown: returns 0 ok, 1 None (start point in no entity), -1 runaway
+int oracle_trace_path(const EuclFlatScene* scene, const double* location, const double* direction, double distance,
+                      double* out_location, double* out_direction) {
+    EuclCamera cam{};
+    bool runaway = false, ok;
+    if (scene->dim == 3) {
+        Tracer<3> tr(*scene, cam, 0.0);
+        Vec<3> l, d;
+        ok = tr.trace_path_unknown(distance, load<3>(location), load<3>(direction), &l, &d, &runaway);
+        for (int k = 0; ok && k < 3; ++k) {
+            out_location[k] = l[k];
+            out_direction[k] = d[k];
+        }
+    } else {
+        Tracer<4> tr(*scene, cam, 0.0);
+        Vec<4> l, d;
+        ok = tr.trace_path_unknown(distance, load<4>(location), load<4>(direction), &l, &d, &runaway);
+        for (int k = 0; ok && k < 4; ++k) {
+            out_location[k] = l[k];
+            out_direction[k] = d[k];
+        }
+    }
+    if (runaway) return -1;
+    return ok ? 0 : 1;
 }
 
 int oracle_entity_inside(const EuclFlatScene* scene, int entity, const double* point) {

@@ -81,6 +81,8 @@ def lib(variant: str = "det") -> C.CDLL:
         h.oracle_detmath_unary.argtypes = [C.c_int, dptr, dptr, C.c_int]
         h.oracle_detmath_atan2.restype = None
         h.oracle_detmath_atan2.argtypes = [dptr, dptr, dptr, C.c_int]
+        h.oracle_trace_path.restype = C.c_int
+        h.oracle_trace_path.argtypes = [C.POINTER(EuclFlatScene), dptr, dptr, C.c_double, dptr, dptr]
         h.oracle_uses_detmath.restype = C.c_int
         _libs[variant] = h
     return _libs[variant]
@@ -111,3 +113,16 @@ def render(env, width: int, height: int, time: float = 0.0, threads: int | None 
         "no_material": int(stats[4]), "csg_runaway": int(stats[5]),
         "level_counts": [int(v) for v in stats[8:8 + levels]],
     }
+
+
+def trace_path(env, location, direction, distance: float, variant: str = "det"):
+    """Universe::trace_path_unknown on the oracle: (location, direction) or None."""
+    dim = env.dim
+    out_l, out_d = (C.c_double * dim)(), (C.c_double * dim)()
+    flat = env.flat
+    rc = lib(variant).oracle_trace_path(C.byref(flat), darr(location), darr(direction), float(distance), out_l, out_d)
+    if rc == 1:
+        return None
+    if rc != 0:
+        raise RuntimeError("oracle_trace_path: runaway")
+    return list(out_l), list(out_d)
