@@ -52,9 +52,10 @@ __device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const V
                                           double& t1) {
     const int n = sv.n_prims;
     const int kind = sv.prim_kind()[prim];
+    const double* __restrict__ rec = sv.planes() + (size_t)prim * kPlaneStride; // AoS: [v0[0..3], s0, s1]
     if (kind == EUCL_PRIM_SPHERE) { // shape.rs:662-670
-        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
-        double radius = sv.prim_s0()[prim];
+        Vec<D> center = load_vec<D>(rec, 1);
+        double radius = rec[4];
         Vec<D> rel = o - center;
         double a = norm_squared(d);
         double b = 2.0 * dot(d, rel);
@@ -62,16 +63,16 @@ __device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const V
         return quadratic_hits(a, b, c, t0, t1);
     }
     if (kind == EUCL_PRIM_HYPERPLANE || kind == EUCL_PRIM_HALFSPACE) { // shape.rs:788-793
-        Vec<D> nrm = load_vec<D>(sv.prim_v0() + prim, n);
-        double t = -(dot(nrm, o) + sv.prim_s0()[prim]) / dot(nrm, d);
+        Vec<D> nrm = load_vec<D>(rec, 1);
+        double t = -(dot(nrm, o) + rec[4]) / dot(nrm, d);
         if (t < 0.0) return 0; // NaN and +inf pass, exactly like the reference
         t0 = t;
         return 1;
     }
     if (kind == EUCL_PRIM_CYLINDER) { // shape.rs:946-953
-        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
+        Vec<D> center = load_vec<D>(rec, 1);
         Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
-        double radius = sv.prim_s0()[prim];
+        double radius = rec[4];
         Vec<D> a_vec = d - axis * dot(d, axis);
         Vec<D> delta = o - center;
         Vec<D> c_vec = delta - axis * dot(delta, axis);
@@ -88,18 +89,19 @@ template <int D>
 __device__ __forceinline__ bool prim_inside(const SceneView& sv, int prim, const Vec<D>& p) {
     const int n = sv.n_prims;
     const int kind = sv.prim_kind()[prim];
+    const double* __restrict__ rec = sv.planes() + (size_t)prim * kPlaneStride;
     if (kind == EUCL_PRIM_HALFSPACE) {
-        double r = dot(load_vec<D>(sv.prim_v0() + prim, n), p) + sv.prim_s0()[prim];
-        return sv.prim_s1()[prim] == rust_signum(r);
+        double r = dot(load_vec<D>(rec, 1), p) + rec[4];
+        return rec[5] == rust_signum(r);
     }
     if (kind == EUCL_PRIM_SPHERE) {
-        double radius = sv.prim_s0()[prim];
-        return norm_squared(load_vec<D>(sv.prim_v0() + prim, n) - p) <= radius * radius;
+        double radius = rec[4];
+        return norm_squared(load_vec<D>(rec, 1) - p) <= radius * radius;
     }
     if (kind == EUCL_PRIM_CYLINDER) {
-        Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
+        Vec<D> center = load_vec<D>(rec, 1);
         Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
-        double radius = sv.prim_s0()[prim];
+        double radius = rec[4];
         Vec<D> on_axis = axis * dot(axis, p - center) + center;
         return norm_squared(p - on_axis) <= radius * radius;
     }
@@ -407,6 +409,12 @@ __device__ __forceinline__ bool csg_first(const SceneView& sv, int first, int ro
             } else if ((nd.b & 0x4000) && count <= kPlaneChainMax) {
                 unsigned long long L = 0ull;
                 c = plane_chain<D>(sv, nd.b >> 16, nd.a, count, o, d, n == root, ts, ts_stride, L);
+                if (first == root) { // the chain is the entity's whole shape: its first item is the answer
+                    if (c == 0) return false;
+                    const int idx = (int)(L & 15ull);
+                    out = CHit{ts[idx * ts_stride], nd.a + idx, 0};
+                    return true;
+                }
                 for (int i = 0; i < c; ++i) {
                     const int idx = (int)((L >> (4 * i)) & 15ull);
                     arena[top + i] = CHit{ts[idx * ts_stride], nd.a + idx, 0};
