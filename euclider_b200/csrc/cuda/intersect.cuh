@@ -13,7 +13,7 @@
 
 namespace eucl {
 
-constexpr int CSG_ARENA = 128;     // compact hits per thread (scene_create validates programs against it)
+constexpr int CSG_ARENA = 256;     // compact hits per thread (scene_create validates programs against it)
 constexpr int CSG_LIST_STACK = 16; // nesting depth of pending child lists
 constexpr int CHAIN_ROOT_CAP = 32; // hits of a chain that is an entity's whole shape (<= 16 leaves)
 
