@@ -75,6 +75,16 @@ struct EuclScene {
     DeviceBuffer hit_ids;  // device hit-id map for eucl_render
     DeviceBuffer order;    // per-bin node lists of the level being shaded
     DeviceBuffer path_io;  // eucl_trace_path staging
+    DeviceBuffer rorder;   // per-reach-key node lists of the next level
+    int n_cull = 0;
+    // Grouping rays by reach key pays on scenes whose deep levels bounce around a few bounded objects
+    // (3d_room: -13 % frame time) and costs a little elsewhere, so it is auto-tuned per scene: the
+    // first two retry-free frames run with and without it, the faster setting is kept.  The picture
+    // does not depend on it.  EUCL_BIN_RAYS=0/1 forces a setting.
+    int ray_bins_mode = -1;      // -1 undecided, 0 off, 1 on
+    bool ray_bins_now = true;    // setting of the frame being rendered
+    float tune_ms[2] = {0.f, 0.f};
+    int warm_frames = 0;
     int n_entities = 0;
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
@@ -83,7 +93,7 @@ struct EuclScene {
 
 namespace {
 
-constexpr int kSmallInts = 4 * (EUCL_MAX_LEVELS + 1) + 16 + (EUCL_MAX_LEVELS + 1) * kMaxBins; // count, level_off, flags, bins
+constexpr int kSmallInts = 4 * (EUCL_MAX_LEVELS + 1) + 16 + (EUCL_MAX_LEVELS + 1) * (kMaxBins + kRayBins); // count, level_off, flags, bins
 struct SmallLayout {                                        // one per chunk, in ints
     static constexpr int count = 0;
     static constexpr int level_off = EUCL_MAX_LEVELS + 1;
@@ -92,7 +102,8 @@ struct SmallLayout {                                        // one per chunk, in
     static constexpr int undefined64 = overflow + 2;                  // 8-byte aligned (even index)
     static constexpr int mega64 = undefined64 + 2;                    // (EUCL_MAX_LEVELS + 1) x u64
     static constexpr int bins = mega64 + 2 * (EUCL_MAX_LEVELS + 1);       // [level][kMaxBins]
-    static constexpr int total = bins + (EUCL_MAX_LEVELS + 1) * kMaxBins;
+    static constexpr int rbins = bins + (EUCL_MAX_LEVELS + 1) * kMaxBins; // [level][kRayBins]
+    static constexpr int total = rbins + (EUCL_MAX_LEVELS + 1) * kRayBins;
 };
 static_assert(SmallLayout::undefined64 % 2 == 0, "u64 counters must be 8-byte aligned");
 static_assert(SmallLayout::total <= kSmallInts, "small buffer layout");
@@ -402,6 +413,7 @@ void eucl_scene_destroy(EuclScene* s) {
     s->hit_ids.release();
     s->order.release();
     s->path_io.release();
+    s->rorder.release();
     if (s->h_small) cudaFreeHost(s->h_small);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -534,6 +546,12 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     h.n_nodes = (int)mb.out.size();
     h.off_nodes = w.put(mb.out.data(), mb.out.size());
     h.off_bounds = w.put(bounds.data(), bounds.size());
+    for (int e = 0; e < flat->n_entities && h.n_cull < 4; ++e) { // entities worth a reach-key bit
+        const EuclEntity& de = dev_entities[(size_t)e];
+        if (de.surface >= 0 && mb.out[(size_t)de.node_root].kind != M_PRIM && bounds[(size_t)de.node_root].r2 >= 0.0)
+            h.cull_root[h.n_cull++] = de.node_root;
+    }
+    s->n_cull = h.n_cull;
     h.off_entities = w.put(dev_entities.data(), dev_entities.size());
     h.off_materials = w.put(flat->materials, (size_t)flat->n_materials);
     h.off_transforms = w.put(flat->transforms, (size_t)flat->n_transforms);
@@ -641,6 +659,9 @@ Workspace carve(EuclScene* s, int dim, int cap) {
     ws.order = (int32_t*)s->order.ptr;
     const bool bin = s->order.ptr != nullptr;
     ws.n_bins = bin ? 2 * s->n_entities + 1 : 1;
+    ws.rbin_count = small + SmallLayout::rbins;
+    ws.rorder = (int32_t*)s->rorder.ptr;
+    ws.ray_bins = s->rorder.ptr != nullptr && s->ray_bins_now ? 1 : 0;
     return ws;
 }
 
@@ -654,6 +675,12 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     const uint32_t my_rows = eucl_band_rows_for_rank(o);
     EuclStats st{};
     st.levels = cam->max_depth + 1;
+    {
+        const int forced = env_int("EUCL_BIN_RAYS", -1);
+        if (forced >= 0) s->ray_bins_mode = forced ? 1 : 0;
+        if (s->ray_bins_mode >= 0) s->ray_bins_now = s->ray_bins_mode == 1;
+        else s->ray_bins_now = s->tune_ms[1] == 0.f; // first measure "on", then "off"
+    }
     EUCL_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (my_rows > 0) {
         // chunking: whole local rows, about EUCL_CHUNK_PIXELS primaries per chunk
@@ -684,6 +711,8 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     EUCL_CUDA(cudaStreamSynchronize(s->stream));
                     EUCL_CUDA(s->nodes.ensure(arena_bytes(dim, (size_t)want)));
                     s->arena_capacity = (int)want;
+                    if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1))
+                        EUCL_CUDA(s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want));
                     // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
                     if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && 2 * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1))
                         EUCL_CUDA(s->order.ensure(sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * (size_t)want));
@@ -702,8 +731,25 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     cudaEventRecord(s->prof_events[prof_family.size()], s->stream);
                     prof_family.push_back(family);
                 };
+                // EUCL_DEBUG_SYNC=1: synchronise after every launch and name the one that faulted;
+                // EUCL_POISON=1: fill the work buffers with 0x7F bytes (huge positive indices) first, so that a read of anything this
+                // frame did not write turns into a deterministic fault instead of depending on stale data
+                const bool debug_sync = env_int("EUCL_DEBUG_SYNC", 0) != 0;
+                std::string fault;
+                auto dbg = [&](const char* what, int level) {
+                    if (!debug_sync || !fault.empty()) return;
+                    cudaError_t e = cudaStreamSynchronize(s->stream);
+                    if (e == cudaSuccess) e = cudaGetLastError();
+                    if (e != cudaSuccess) fault = std::string(what) + " level " + std::to_string(level) + ": " + cudaGetErrorString(e);
+                };
+                if (env_int("EUCL_POISON", 0)) {
+                    cudaMemsetAsync(s->nodes.ptr, 0x7F, s->nodes.bytes, s->stream);
+                    if (s->order.ptr) cudaMemsetAsync(s->order.ptr, 0x7F, s->order.bytes, s->stream);
+                    if (s->rorder.ptr) cudaMemsetAsync(s->rorder.ptr, 0x7F, s->rorder.bytes, s->stream);
+                }
                 mark(-1);
                 launch_camera_entity(dim, l, fp, ws);
+                dbg("k_camera_entity", 0);
                 st.launches += 1;
                 if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) {
                     if (cam->max_depth > 24) return fail(EUCL_ERR_SCENE_LIMIT, "megakernel pipeline supports max_depth <= 24");
@@ -712,22 +758,32 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     st.launches += 1;
                 } else {
                     launch_raygen(dim, l, fp, cp, ws, d_hit);
+                    dbg("k_raygen", 0);
                     mark(0);
                     for (int level = 0; level < (int)cam->max_depth; ++level) {
                         launch_intersect(dim, l, ws, level);
+                        dbg("k_intersect", level);
                         mark(1);
                         launch_shade(dim, l, fp, cp, ws, level, d_hit);
+                        dbg("k_shade", level);
                         mark(2);
                     }
                     launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
+                    dbg("k_shade", (int)cam->max_depth);
                     mark(2);
                     if (tree_resolve) {
                         launch_final_tree(l, fp, cp, ws, d_rgb);
+                        dbg("k_final_tree", 0);
                     } else {
-                        for (int level = (int)cam->max_depth - 1; level >= 1; --level) launch_resolve(dim, l, ws, level);
+                        for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
+                            launch_resolve(dim, l, ws, level);
+                            dbg("k_resolve", level);
+                        }
                         launch_final(dim, l, fp, cp, ws, d_rgb);
+                        dbg("k_final", 0);
                     }
                     mark(3);
+                    if (!fault.empty()) return fail(EUCL_ERR_CUDA, "EUCL_DEBUG_SYNC: " + fault);
                     st.launches += 3 + 2 * cam->max_depth + (tree_resolve || cam->max_depth == 0 ? 0 : cam->max_depth - 1);
                 }
                 EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
@@ -741,6 +797,8 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                                   : prof_family[k] == 2 ? &st.ms_shade : &st.ms_resolve;
                     *slot += ms;
                 }
+                if (s->h_small[SmallLayout::overflow] == 2)
+                    return fail(EUCL_ERR_CUDA, "internal error: a queue index list and its level count disagree");
                 if (s->h_small[SmallLayout::overflow]) {
                     // levels after the overflowing one were skipped, so the counts are a lower bound only
                     long long need = 0;
@@ -769,6 +827,14 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     EUCL_CUDA(cudaEventRecord(s->ev[1], s->stream));
     EUCL_CUDA(cudaEventSynchronize(s->ev[1]));
     EUCL_CUDA(cudaEventElapsedTime(&st.ms_total, s->ev[0], s->ev[1]));
+    if (s->ray_bins_mode < 0 && st.retries == 0 && my_rows > 0 && o->pipeline == EUCL_PIPELINE_WAVEFRONT) {
+        if (s->n_cull == 0) {
+            s->ray_bins_mode = 0;
+        } else if (s->warm_frames++ >= 1) { // skip the very first frame (allocations, cold caches)
+            s->tune_ms[s->ray_bins_now ? 1 : 0] = st.ms_total;
+            if (s->tune_ms[0] > 0.f && s->tune_ms[1] > 0.f) s->ray_bins_mode = s->tune_ms[1] < s->tune_ms[0] ? 1 : 0;
+        }
+    }
     if (stats) *stats = st;
     return EUCL_OK;
 }

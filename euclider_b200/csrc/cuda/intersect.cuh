@@ -207,6 +207,18 @@ __device__ __forceinline__ bool ray_misses(const Bound& bnd, const Vec<D>& o, co
     return (b * b - dd * c < 0.0) || (c > 0.0 && b > 0.0);
 }
 
+// Reach key of a ray: which of the scene's bounded, non-trivial entities its half-line can reach.
+// Rays with equal keys take the same branches in closest_hit, so the rays of a level are walked
+// grouped by this key (kernels.cu).  Purely an ordering hint: results do not depend on it.
+template <int D>
+__device__ __forceinline__ int reach_key(const SceneView& sv, const Vec<D>& o, const Vec<D>& d) {
+    const double dd = dot(d, d);
+    int key = 0;
+    for (int k = 0; k < sv.n_cull; ++k)
+        if (!ray_misses<D>(sv.bounds()[sv.cull_root[k]], o, d, dd)) key |= 1 << k;
+    return key;
+}
+
 // Hit list of a chain macro node, "up to the first None", written to L (capacity cap; T is scratch
 // of the same size).  Step k merges the list so far (stream A) with the hits of leaf k (stream B)
 // exactly like IntersectionIterator / UnionIterator (shape.rs:212-340):

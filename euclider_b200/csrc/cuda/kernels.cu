@@ -262,7 +262,11 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
 // K2: closest hit of every ray of one level.
 template <int D>
 __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level) {
-    if (*ws.overflow) return; // an earlier level did not fit: the host grows the arena and retries
+    // an earlier level did not fit: the host grows the arena and retries.  One decision per block (see k_shade).
+    __shared__ int s_skip;
+    if (threadIdx.x == 0) s_skip = *ws.overflow != 0;
+    __syncthreads();
+    if (s_skip) return;
     const int off = ws.level_off[level], cnt = ws.count[level];
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.level_off[level + 1] = off + cnt;
     if (blockIdx.x * blockDim.x >= cnt) return;
@@ -270,10 +274,33 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
     double* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
+    // levels >= 1: the shade kernel of the previous level grouped this level's rays by reach key
+    __shared__ int s_rprefix[kRayBins + 1];
+    const bool grouped = ws.ray_bins != 0 && level > 0;
+    if (grouped && threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < kRayBins; ++b) {
+            s_rprefix[b] = acc;
+            acc += ws.rbin_count[level * kRayBins + b];
+        }
+        s_rprefix[kRayBins] = acc;
+    }
+    __syncthreads();
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cnt; base += stride) {
         const int i = base + (int)lane;
-        const int node = off + i;
-        const bool valid = i < cnt && ws.ray_cur[node] >= 0;
+        int node = off + i;
+        bool valid = i < cnt;
+        if (grouped && valid) {
+            int b = 0;
+            while (b < kRayBins - 1 && i >= s_rprefix[b + 1]) ++b;
+            node = ws.rorder[(size_t)b * ws.capacity + (i - s_rprefix[b])];
+            if (i >= s_rprefix[kRayBins] || node < off || node >= off + cnt) { // must not happen: reported, never dereferenced
+                *ws.overflow = 2;
+                valid = false;
+                node = off;
+            }
+        }
+        valid = valid && ws.ray_cur[node] >= 0;
         int ent = -1;
         bool exiting_flag = false;
         if (valid) {
@@ -306,12 +333,19 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
 
 // K3: shade every node of one level and append its children to the next level.  Children are
 // appended with one atomicAdd per warp (ballot + popc ranks).
-template <int D>
+template <int D, bool RAY_BINS>
 __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
                                                   Workspace ws, int level, int32_t* __restrict__ hit_ids_out) {
     const int off = ws.level_off[level], cnt = ws.count[level];
     if (blockIdx.x * blockDim.x >= cnt) return;
-    if (level > 0 && *ws.overflow) return; // set by an EARLIER kernel (level 0 always fits); see k_intersect
+    // An overflow flagged by an EARLIER kernel means this level's queue is incomplete: skip it (the host
+    // retries with a larger arena).  Blocks of THIS launch set the flag too, so the decision must be taken
+    // once per block: threads reading the flag on their own could disagree, and the ones that left would
+    // be missing from the cooperative scene staging below (a partially staged scene = wild table offsets).
+    __shared__ int s_skip;
+    if (threadIdx.x == 0) s_skip = level > 0 && *ws.overflow != 0;
+    __syncthreads();
+    if (s_skip) return;
     const SceneView& sv = stage_scene(blob);
     const bool last_level = level >= fp.max_depth; // depth 0: background without intersecting (mod.rs:157,183)
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
@@ -338,6 +372,11 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
             int b = 0;
             while (g >= s_prefix[b + 1]) ++b;
             node = ws.order[(size_t)b * ws.capacity + (g - s_prefix[b])];
+            if (node < off || node >= off + cnt) { // must not happen: reported, never dereferenced
+                *ws.overflow = 2;
+                valid = false;
+                node = off;
+            }
         } else if (valid) {
             valid = ws.ray_cur[node] >= 0;
         }
@@ -366,6 +405,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
                 shaded = true;
             }
         }
+        int so_tchild = -1, so_rchild = -1;
         // warp-aggregated append of the children to level + 1: one atomicAdd per warp
         const unsigned tmask = __ballot_sync(0xffffffffu, so.t_emit), rmask = __ballot_sync(0xffffffffu, so.r_emit);
         const int nt = __popc(tmask), total = nt + __popc(rmask);
@@ -387,6 +427,8 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
                 rchild = next_off + slot + nt + __popc(rmask & lt);
                 store_ray<D>(ws, rchild, so.r.o, so.r.d, so.r.cur);
             }
+            so_tchild = tchild;
+            so_rchild = rchild;
             unsigned flags = so.flags;
             if (flags & NODE_HAS_SC) {
                 store_res(ws, node, so.sc);
@@ -397,6 +439,25 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
                 atomicAdd(ws.undefined_count, 1ull);
             }
             ws.meta[node] = NodeMeta{so.ratio, tchild, rchild, so.q, flags};
+        }
+        if (RAY_BINS) {
+            // group the NEXT level's rays by reach key (one atomicAdd per warp and distinct key, twice:
+            // transmitted children, then reflected ones)
+#pragma unroll 1
+            for (int which = 0; which < 2; ++which) {
+                const int child = which == 0 ? so_tchild : so_rchild;
+                const unsigned active = __ballot_sync(0xffffffffu, child >= 0);
+                if (child >= 0) {
+                    const ChildRay<D>& cr = which == 0 ? so.t : so.r;
+                    const int key = reach_key<D>(sv, cr.o, cr.d);
+                    const unsigned peers = __match_any_sync(active, key);
+                    const int leader = __ffs(peers) - 1;
+                    int s2 = 0;
+                    if ((int)lane == leader) s2 = atomicAdd(&ws.rbin_count[(level + 1) * kRayBins + key], __popc(peers));
+                    s2 = __shfl_sync(peers, s2, leader);
+                    ws.rorder[(size_t)key * ws.capacity + s2 + __popc(peers & ((1u << lane) - 1u))] = child;
+                }
+            }
         }
     }
 }
@@ -777,9 +838,15 @@ void launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) 
 }
 void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
                   int32_t* hit_ids_out) {
-    EUCL_DISPATCH_DIM(dim,
-                      (k_shade<3><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
-                      (k_shade<4><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
+    if (ws.ray_bins && level + 1 < fp.max_depth) { // the next level will be intersected: group its rays
+        EUCL_DISPATCH_DIM(dim,
+                          (k_shade<3, true><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
+                          (k_shade<4, true><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
+    } else {
+        EUCL_DISPATCH_DIM(dim,
+                          (k_shade<3, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
+                          (k_shade<4, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
+    }
 }
 void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level) {
     (void)dim;
@@ -820,8 +887,10 @@ cudaError_t configure_kernels(size_t smem_bytes) {
     EUCL_SET_SMEM(k_raygen<4>);
     EUCL_SET_SMEM(k_intersect<3>);
     EUCL_SET_SMEM(k_intersect<4>);
-    EUCL_SET_SMEM(k_shade<3>);
-    EUCL_SET_SMEM(k_shade<4>);
+    EUCL_SET_SMEM((k_shade<3, true>));
+    EUCL_SET_SMEM((k_shade<4, true>));
+    EUCL_SET_SMEM((k_shade<3, false>));
+    EUCL_SET_SMEM((k_shade<4, false>));
     EUCL_SET_SMEM(k_megakernel<3>);
     EUCL_SET_SMEM(k_megakernel<4>);
     EUCL_SET_SMEM(k_trace_path<3>);

@@ -83,6 +83,10 @@ struct Workspace {
     int32_t _pad2;
     int32_t* bin_count;  // [EUCL_MAX_LEVELS + 1][kMaxBins] nodes per (level, hit-entity bin)
     int32_t* order;      // [n_bins][capacity] node ids of the current level grouped by bin (reused per level)
+    int32_t ray_bins;    // 1: the rays of levels >= 1 are walked grouped by reach key (see SceneHeader::cull_root)
+    int32_t _pad3;
+    int32_t* rbin_count; // [EUCL_MAX_LEVELS + 1][kRayBins]
+    int32_t* rorder;     // [kRayBins][capacity] node ids of the NEXT level grouped by reach key
     unsigned long long* undefined_count;   // nodes that touched a corner the reference leaves undefined
     unsigned long long* mega_level_counts; // [EUCL_MAX_LEVELS + 1] nodes per level, megakernel pipeline only
 };
@@ -98,6 +102,7 @@ struct Launch {
 #define EUCL_BLOCK 128
 #endif
 constexpr int kBlock = EUCL_BLOCK;
+constexpr int kRayBins = 16; // 2^4 reach keys
 constexpr int kMaxBins = 64; // shade-coherence bins (miss, then 2 per entity: entering / exiting); larger scenes shade unbinned
 
 // kernels.cu

@@ -27,6 +27,11 @@ struct SceneHeader {
     int32_t off_nodes, off_entities, off_materials, off_transforms, off_expr_ops;
     int32_t off_surfaces, off_color_ops, off_mapped, off_textures, off_tex_objects, off_perlin;
     int32_t off_planes, off_bounds;
+    // "reach" key of a ray: bit k set when the ray can reach cull_root[k] (macro root nodes of up to 4 entities
+    // that own a bounding sphere and are not a bare primitive); used to group the rays of a level
+    int32_t n_cull;
+    int32_t cull_root[4];
+    int32_t _pad2[3];
 };
 static_assert(sizeof(SceneHeader) % 16 == 0, "header must keep 16-byte alignment");
 
@@ -47,6 +52,7 @@ extern __shared__ __align__(16) unsigned char g_smem[];
 // Byte offsets (from g_smem) of the staged tables; lives at the start of shared memory.
 struct SceneView {
     int dim, n_prims, n_nodes, n_entities, n_surfaces, background;
+    int n_cull, cull_root[4];
     uint32_t o_prim_kind, o_prim_v0, o_prim_v1, o_prim_s0, o_prim_s1, o_planes, o_nodes, o_entities, o_materials,
         o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin, o_bounds;
 #if defined(__CUDACC__)
@@ -96,6 +102,8 @@ __device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restric
         view->n_entities = h->n_entities;
         view->n_surfaces = h->n_surfaces;
         view->background = h->background;
+        view->n_cull = h->n_cull;
+        for (int k = 0; k < 4; ++k) view->cull_root[k] = h->cull_root[k];
         view->o_prim_kind = base + h->off_prim_kind;
         view->o_prim_v0 = base + h->off_prim_v0;
         view->o_prim_v1 = base + h->off_prim_v1;
