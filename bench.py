@@ -359,11 +359,12 @@ def main():
         roofline = {"bound": "fp64_issue", "unit": "Tflop/s", "peak": peak, "peak_source": "measured live (DADD/DMUL microbenchmark)",
                     "peak_dfma_tops": dfma.value, "traffic": None, "flops_per_segment": f_scene}
         if args.scene == "3d_room" and (width, height) == (3840, 2160):
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_intersect launch (level 0 of a 4 Mi-pixel chunk,
-            # 4.19 M rays) from the committed ncu --set full capture (profiles/README.md); algorithmic bytes of that
-            # launch: none beyond its 212 B/node queue records (the frame itself is 3 B/pixel, written by k_final)
-            roofline["traffic"] = 219.868928e6 + 264.643072e6
-            roofline["traffic_note"] = "one level-0 k_intersect launch, 4.19 M rays, ncu capture of round 1"
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_intersect launch (level 8 of a whole-frame chunk,
+            # 4.15 M rays) from the committed ncu --set full capture (profiles/r1b_ncu_k_intersect_level8.txt).
+            # Algorithmic bytes of that launch: none beyond its queue records (ray 52 B in, hit 64 B out per ray =
+            # 482 MB); the frame itself is 3 B/pixel, written by k_final.
+            roofline["traffic"] = 368.689920e6 + 303.072512e6
+            roofline["traffic_note"] = "one level-8 k_intersect launch, 4.15 M rays, ncu --set full capture (profiles/r1b_*)"
         if prof is not None and prof["ms_intersect"] > 0:
             achieved = prof["segments"] * f_scene / (prof["ms_intersect"] * 1e-3) / 1e12
             roofline.update({"kernel": "k_intersect (all levels of one frame)", "achieved": achieved, "frac": achieved / peak,
