@@ -442,14 +442,12 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
         }
         if (RAY_BINS) {
             // group the NEXT level's rays by reach key (one atomicAdd per warp and distinct key, twice:
-            // transmitted children, then reflected ones)
-#pragma unroll 1
-            for (int which = 0; which < 2; ++which) {
-                const int child = which == 0 ? so_tchild : so_rchild;
+            // transmitted children, then reflected ones).  Called with the members of `so` directly: choosing
+            // between so.t and so.r through a reference would force both into local memory.
+            auto bin_child = [&](int child, const Vec<D>& co, const Vec<D>& cd) {
                 const unsigned active = __ballot_sync(0xffffffffu, child >= 0);
                 if (child >= 0) {
-                    const ChildRay<D>& cr = which == 0 ? so.t : so.r;
-                    const int key = reach_key<D>(sv, cr.o, cr.d);
+                    const int key = reach_key<D>(sv, co, cd);
                     const unsigned peers = __match_any_sync(active, key);
                     const int leader = __ffs(peers) - 1;
                     int s2 = 0;
@@ -457,7 +455,9 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
                     s2 = __shfl_sync(peers, s2, leader);
                     ws.rorder[(size_t)key * ws.capacity + s2 + __popc(peers & ((1u << lane) - 1u))] = child;
                 }
-            }
+            };
+            bin_child(so_tchild, so.t.o, so.t.d);
+            bin_child(so_rchild, so.r.o, so.r.d);
         }
     }
 }
