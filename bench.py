@@ -374,7 +374,7 @@ def main():
             achieved = value * 1e6 * f_scene / 1e12
             roofline.update({"kernel": "whole frame", "achieved": achieved, "frac": achieved / (peak * world)})
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
             try:
                 c_segs, c_secs, desc, threads = oracle_sample(env, width, height, args.time, rows_per_block=args.ref_rows)
                 cpu = {"value": c_segs / c_secs / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}

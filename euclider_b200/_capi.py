@@ -140,6 +140,10 @@ PROTOTYPES = {
                                      C.c_void_p, C.POINTER(EuclStats)]),
     "eucl_trace_path": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "eucl_camera_rotate_yaw": (C.c_int, [C.POINTER(EuclCamera), C.c_double, C.c_int]),
+    "eucl_camera_rotate_pitch": (C.c_int, [C.POINTER(EuclCamera), C.c_double, C.c_int]),
+    "eucl_camera_rotate_roll": (C.c_int, [C.POINTER(EuclCamera), C.c_double]),
+    "eucl_camera_rotate_plane4": (C.c_int, [C.POINTER(EuclCamera), C.c_int, C.c_int, C.c_double]),
     "eucl_device_malloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "eucl_device_free": (C.c_int, [C.c_int, C.c_void_p]),
     "eucl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

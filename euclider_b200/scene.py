@@ -163,6 +163,22 @@ class Environment:
             self.camera.location[k] = res[0][k]
         return True
 
+    # The view-turning part of the reference's camera `update` (d3/entity/camera.rs:94-145,303-350;
+    # d4/entity/camera.rs:68-130).  The reference derives the angles from mouse deltas and held keys;
+    # here the caller passes them (radians).  `kind` names the reference camera type being mimicked.
+    def rotate_yaw(self, angle: float, kind: str = "PitchYawCamera3") -> None:
+        check(lib().eucl_camera_rotate_yaw(C.byref(self.camera), float(angle), 0 if kind == "PitchYawCamera3" else 1))
+
+    def rotate_pitch(self, angle: float, kind: str = "PitchYawCamera3") -> None:
+        check(lib().eucl_camera_rotate_pitch(C.byref(self.camera), float(angle), 1 if kind == "PitchYawCamera3" else 0))
+
+    def rotate_roll(self, angle: float) -> None:
+        check(lib().eucl_camera_rotate_roll(C.byref(self.camera), float(angle)))
+
+    def rotate_plane4(self, axis_a: int, axis_b: int, angle: float) -> None:
+        """FreeCamera4: rotation in the plane of two camera axes (0 forward, 1 left, 2 up, 3 ana)."""
+        check(lib().eucl_camera_rotate_plane4(C.byref(self.camera), int(axis_a), int(axis_b), float(angle)))
+
     # -- plumbing ----------------------------------------------------------------------------------
     @property
     def flat(self) -> EuclFlatScene:

@@ -317,6 +317,21 @@ int eucl_render_device(EuclScene* scene, const EuclCamera* camera, const EuclRen
 int eucl_trace_path(EuclScene* scene, const double* location, const double* direction, double distance,
                     double* out_location, double* out_direction);
 
+/* Camera rotations: the view-turning part of the reference's per-frame Camera::update, on an EuclCamera pose
+ * (host arithmetic; the translation part is eucl_trace_path).  Angles in radians.  Replaces
+ * PitchYawCamera3::rotate_yaw_static / rotate_pitch_static (src/universe/d3/entity/camera.rs:110-136),
+ * FreeCamera3::rotate_yaw_static / rotate_roll_static (:329-337) and the matrix part of
+ * FreeCamera4::update_rotation (src/universe/d4/entity/camera.rs:68-130).
+ *   rotate_yaw:    about_up = 0: forward and up turn about +z (PitchYawCamera3); 1: forward turns about up (FreeCamera3)
+ *   rotate_pitch:  about forward x up; snap = 1 stops at straight up / down (PitchYawCamera3), 0 = FreeCamera3
+ *   rotate_roll:   up turns about forward (FreeCamera3)
+ *   rotate_plane4: rotation in the plane of two of the camera's own axes (0 forward, 1 left, 2 up, 3 ana), then
+ *                  reorthonormalize_4 (src/util.rs:309-322) */
+int eucl_camera_rotate_yaw(EuclCamera* camera, double angle, int about_up);
+int eucl_camera_rotate_pitch(EuclCamera* camera, double angle, int snap);
+int eucl_camera_rotate_roll(EuclCamera* camera, double angle);
+int eucl_camera_rotate_plane4(EuclCamera* camera, int axis_a, int axis_b, double angle);
+
 /* Plain device allocations (cudaMalloc / cudaFree) for buffers that are shared through eucl_ipc_*:
  * an IPC handle must name the base of its own allocation, which framework allocators that carve
  * tensors out of large pools cannot guarantee. */
