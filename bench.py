@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--max-depth", type=int, default=0)
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--band-rows", type=int, default=16)
-    ap.add_argument("--ref-rows", type=int, default=8)
+    ap.add_argument("--ref-rows", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: ranks store their rows into GPU 0's frame through CUDA IPC (peer) or NCCL gather")

@@ -177,3 +177,34 @@ def test_tree_resolve_variant_is_identical(built_lib, monkeypatch):
     monkeypatch.setenv("EUCL_TREE_RESOLVE", "1")
     b = env.render((160, 90), time=0.3)
     assert np.array_equal(a.data, b.data) and b.stats["launches"] < a.stats["launches"]
+
+
+@pytest.mark.parametrize("name", ["3d_room", "3d_hallways"])
+def test_turned_cameras_3d(built_lib, oracle, name):
+    """Poses reached through the rotation entry points (yaw, pitch, roll: csrc/host/camera.cc): oblique
+    camera frames through ray generation, both grouping modes of the wavefront (the first frames of a scene
+    alternate between them while it tunes itself)."""
+    env = load(name)
+    env.rotate_yaw(0.4)
+    env.rotate_pitch(-0.25)
+    env.rotate_roll(0.3)
+    ref = oracle.render(env, 128, 72, time=0.5, variant="det")
+    for _ in range(4):
+        assert_exact(env.render((128, 72), time=0.5, want_hit_ids=True), *ref)
+
+
+def test_turned_camera_4d(built_lib, oracle):
+    env = load("4d_room")
+    env.rotate_plane4(0, 3, 0.35)  # forward towards ana: the W axis comes into view
+    env.rotate_plane4(1, 2, -0.2)
+    ref = oracle.render(env, 128, 72, time=0.0, variant="det")
+    assert_exact(env.render((128, 72), time=0.0, want_hit_ids=True), *ref)
+
+
+def test_ray_grouping_modes_are_identical(built_lib, oracle, monkeypatch):
+    """EUCL_BIN_RAYS only reorders the rays of a level: same picture, same counts, either way."""
+    env = load("3d_room")
+    ref = oracle.render(env, 160, 90, time=0.75, variant="det")
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EUCL_BIN_RAYS", mode)
+        assert_exact(load("3d_room").render((160, 90), time=0.75, want_hit_ids=True), *ref)
