@@ -683,39 +683,70 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     }
     EUCL_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (my_rows > 0) {
-        // chunking: whole local rows, about EUCL_CHUNK_PIXELS primaries per chunk
-        const long long chunk_pixels_target = std::max(1, env_int("EUCL_CHUNK_PIXELS", 1 << 22));
+        // chunking: whole local rows, about EUCL_CHUNK_PIXELS primaries per chunk.  Large chunks are faster (longer
+        // levels, fewer host round trips: 4d_room 7680x4320 renders 10 % faster as one chunk than as eight), so the
+        // default covers an 8K frame; the chunk shrinks by itself when its arena would not fit (2^31 nodes, the
+        // memory budget, or an allocation failure).
+        const long long chunk_pixels_target = std::max(1, env_int("EUCL_CHUNK_PIXELS", 1 << 25));
         int rows_per_chunk = (int)std::max<long long>(1, chunk_pixels_target / width);
         rows_per_chunk = std::min<int>(rows_per_chunk, (int)my_rows);
-        const long long chunk_pixels = (long long)rows_per_chunk * width;
-        if (chunk_pixels > (1ll << 30)) return fail(EUCL_ERR_INVALID_ARGUMENT, "frame rows too wide");
+        if ((long long)width > (1ll << 30)) return fail(EUCL_ERR_INVALID_ARGUMENT, "frame rows too wide");
         EUCL_CUDA(s->small.ensure(sizeof(int32_t) * kSmallInts));
         if (s->arena_factor <= 0.0) s->arena_factor = std::max(1.0, (double)env_int("EUCL_ARENA_FACTOR_X10", 45) / 10.0);
         Launch l{s->stream, s->d_blob, s->smem_bytes, s->sm_count * env_int("EUCL_BLOCKS_PER_SM", 8)};
         const bool tree_resolve = env_int("EUCL_TREE_RESOLVE", 0) != 0; // 1: one pointer-chasing kernel instead of the level-by-level k_resolve launches (fewer launches, but 3x slower on glass scenes: measured)
+        const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
+        // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
+        const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && 2 * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
+        auto workspace_bytes = [&](size_t cap) {
+            return arena_bytes(dim, cap) + (want_rorder ? sizeof(int32_t) * (size_t)kRayBins * cap : 0) +
+                   (want_order ? sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * cap : 0);
+        };
 
-        for (int row0 = 0; row0 < (int)my_rows; row0 += rows_per_chunk) {
+        for (int row0 = 0; row0 < (int)my_rows;) {
             ChunkParams cp{};
             cp.local_row0 = row0;
-            cp.n_rows = std::min<int>(rows_per_chunk, (int)my_rows - row0);
             cp.band_rows = o->band_rows ? (int)o->band_rows : (int)o->height;
             cp.band_rank = (int)o->band_rank;
             cp.band_world = o->band_world ? (int)o->band_world : 1;
             cp.compact_rows = o->compact_rows;
-            cp.n_pixels = cp.n_rows * width;
-            for (;;) { // retry with a larger arena when a level overflowed
-                long long want = (long long)std::ceil((double)chunk_pixels * s->arena_factor) + 1024;
+            for (;;) { // retry with a larger arena when a level overflowed, with a smaller chunk when the arena cannot grow
+                cp.n_rows = std::min<int>(rows_per_chunk, (int)my_rows - row0);
+                cp.n_pixels = cp.n_rows * width;
+                long long want = (long long)std::ceil((double)rows_per_chunk * (double)width * s->arena_factor) + 1024;
                 if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) want = 16;
-                if (want > 0x7fff0000ll) return fail(EUCL_ERR_OUT_OF_MEMORY, "node arena would exceed 2^31 nodes; lower EUCL_CHUNK_PIXELS");
-                if ((int)want > s->arena_capacity) {
+                bool too_big = want > 0x7fff0000ll;
+                if (!too_big && (int)want > s->arena_capacity) {
                     EUCL_CUDA(cudaStreamSynchronize(s->stream));
-                    EUCL_CUDA(s->nodes.ensure(arena_bytes(dim, (size_t)want)));
-                    s->arena_capacity = (int)want;
-                    if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1))
-                        EUCL_CUDA(s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want));
-                    // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
-                    if (o->pipeline == EUCL_PIPELINE_WAVEFRONT && 2 * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1))
-                        EUCL_CUDA(s->order.ensure(sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * (size_t)want));
+                    size_t free_b = 0, total_b = 0;
+                    EUCL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                    const size_t held = s->nodes.bytes + s->order.bytes + s->rorder.bytes;
+                    size_t budget = (size_t)((double)(free_b + held) * 0.85);
+                    const int cap_mb = env_int("EUCL_ARENA_MAX_MB", 0);
+                    if (cap_mb > 0) budget = std::min(budget, (size_t)cap_mb << 20);
+                    too_big = workspace_bytes((size_t)want) > budget;
+                    if (!too_big) {
+                        cudaError_t e = s->nodes.ensure(arena_bytes(dim, (size_t)want));
+                        if (e == cudaSuccess && want_rorder) e = s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want);
+                        if (e == cudaSuccess && want_order) e = s->order.ensure(sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * (size_t)want);
+                        if (e == cudaSuccess) {
+                            s->arena_capacity = (int)want;
+                        } else { // leave a consistent (empty) workspace behind and try a smaller chunk
+                            cudaGetLastError();
+                            s->nodes.release();
+                            s->rorder.release();
+                            s->order.release();
+                            s->arena_capacity = 0;
+                            if (e != cudaErrorMemoryAllocation) return fail(EUCL_ERR_CUDA, std::string("workspace allocation: ") + cudaGetErrorString(e));
+                            too_big = true;
+                        }
+                    }
+                }
+                if (too_big) {
+                    if (rows_per_chunk <= 1)
+                        return fail(EUCL_ERR_OUT_OF_MEMORY, "the node arena of a single row of pixels does not fit in device memory");
+                    rows_per_chunk = (rows_per_chunk + 1) / 2;
+                    continue;
                 }
                 Workspace ws = carve(s, dim, s->arena_capacity);
                 EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));
@@ -811,6 +842,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                 }
                 break;
             }
+            row0 += cp.n_rows;
             st.pixels += (uint64_t)cp.n_pixels;
             // camera in no entity: checkerboard pixels, Universe::trace is never called (mod.rs:385-396)
             const bool traced = s->h_small[SmallLayout::cam_entity] >= 0;

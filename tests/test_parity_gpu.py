@@ -208,3 +208,20 @@ def test_ray_grouping_modes_are_identical(built_lib, oracle, monkeypatch):
     for mode in ("0", "1"):
         monkeypatch.setenv("EUCL_BIN_RAYS", mode)
         assert_exact(load("3d_room").render((160, 90), time=0.75, want_hit_ids=True), *ref)
+
+
+def test_chunks_shrink_to_the_memory_budget(built_lib, oracle, monkeypatch):
+    """A frame whose node arena does not fit the budget is rendered in smaller chunks of rows, not refused
+    (EUCL_ARENA_MAX_MB stands in for a full device); the picture and the counts do not depend on the split."""
+    env = load("3d_room")
+    ref = oracle.render(env, 160, 90, time=0.25, variant="det")
+    whole = env.render((160, 90), time=0.25, want_hit_ids=True)
+    assert_exact(whole, *ref)
+    monkeypatch.setenv("EUCL_ARENA_MAX_MB", "3")
+    split = load("3d_room").render((160, 90), time=0.25, want_hit_ids=True)
+    assert_exact(split, *ref)
+    assert split.stats["launches"] > 2 * whole.stats["launches"]
+    monkeypatch.setenv("EUCL_ARENA_MAX_MB", "1")  # not even one row fits: a status, not a crash
+    with pytest.raises(eb.EuclError) as err:
+        load("3d_room").render((3840, 90), time=0.25)
+    assert err.value.status == -31
