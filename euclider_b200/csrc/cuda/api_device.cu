@@ -695,7 +695,9 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         if (s->arena_factor <= 0.0) s->arena_factor = std::max(1.0, (double)env_int("EUCL_ARENA_FACTOR_X10", 45) / 10.0);
         // queue kernels run as ONE wave of resident CTAs (4 per SM at 128 registers) walking their level with a grid
         // stride: measured faster than 2-8 waves on glass scenes (3d_room 20.7 -> 20.0 ms), equal elsewhere
-        Launch l{s->stream, s->d_blob, s->smem_bytes, s->sm_count * std::max(1, env_int("EUCL_BLOCKS_PER_SM", 4))};
+        Launch l{s->stream, s->d_blob, s->smem_bytes,
+                 s->sm_count * std::max(1, env_int("EUCL_BLOCKS_PER_SM", kResidentThreads / kBlock)),
+                 s->sm_count * std::max(1, env_int("EUCL_MEM_BLOCKS_PER_SM", 8))};
         const bool tree_resolve = env_int("EUCL_TREE_RESOLVE", 0) != 0; // 1: one pointer-chasing kernel instead of the level-by-level k_resolve launches (fewer launches, but 3x slower on glass scenes: measured)
         const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
@@ -948,7 +950,7 @@ int eucl_trace_path(EuclScene* s, const double* location, const double* directio
         h_in[D + k] = direction[k];
     }
     EUCL_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, s->stream));
-    Launch l{s->stream, s->d_blob, s->smem_bytes, 1};
+    Launch l{s->stream, s->d_blob, s->smem_bytes, 1, 1};
     launch_trace_path(D, l, d_in, distance, d_out, d_found);
     double h_out[2 * EUCL_MAX_DIM];
     int h_found = 0;

@@ -17,10 +17,10 @@ namespace {
 // resident CTAs per SM the register allocator must allow (occupancy hides the long FP64
 // div/sqrt dependency chains and the instruction-fetch bubbles of this branchy code)
 #ifndef EUCL_INTERSECT_MIN_BLOCKS
-#define EUCL_INTERSECT_MIN_BLOCKS 4
+#define EUCL_INTERSECT_MIN_BLOCKS (kResidentThreads / kBlock)
 #endif
 #ifndef EUCL_SHADE_MIN_BLOCKS
-#define EUCL_SHADE_MIN_BLOCKS 4
+#define EUCL_SHADE_MIN_BLOCKS (kResidentThreads / kBlock)
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -828,7 +828,7 @@ void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const
 }
 void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                    int32_t* hit_ids_out) {
-    const int grid = grid_for(cp.n_pixels, kBlock, l.grid_max);
+    const int grid = grid_for(cp.n_pixels, kBlock, l.grid_mem);
     EUCL_DISPATCH_DIM(dim, (k_raygen<3><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)),
                       (k_raygen<4><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)));
 }
@@ -850,15 +850,15 @@ void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkPa
 }
 void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level) {
     (void)dim;
-    k_resolve<<<l.grid_max, 256, 0, l.stream>>>(ws, level);
+    k_resolve<<<l.grid_mem, 256, 0, l.stream>>>(ws, level);
 }
 void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                   uint8_t* out_rgb8) {
     (void)dim;
-    k_final<<<grid_for(cp.n_pixels, 256, l.grid_max), 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
+    k_final<<<grid_for(cp.n_pixels, 256, l.grid_mem), 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
 }
 void launch_final_tree(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, uint8_t* out_rgb8) {
-    const int grid = grid_for(cp.n_pixels, 256, l.grid_max);
+    const int grid = grid_for(cp.n_pixels, 256, l.grid_mem);
     if (fp.max_depth < 16) k_final_tree<16><<<grid, 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
     else k_final_tree<EUCL_MAX_LEVELS><<<grid, 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
 }

@@ -95,13 +95,15 @@ struct Launch {
     cudaStream_t stream;
     const uint8_t* blob;
     size_t smem_bytes;
-    int grid_max; // upper bound on blocks for queue kernels
+    int grid_max; // blocks of the compute-bound queue kernels (k_intersect, k_shade): resident CTAs per SM x waves
+    int grid_mem; // blocks of the memory-bound kernels (k_raygen, k_resolve, k_final, 256 threads each)
 };
 
 #ifndef EUCL_BLOCK
-#define EUCL_BLOCK 128
+#define EUCL_BLOCK 256
 #endif
-constexpr int kBlock = EUCL_BLOCK;
+constexpr int kBlock = EUCL_BLOCK;          // threads per CTA of the scene-walking kernels
+constexpr int kResidentThreads = 512;       // per SM at 128 registers per thread (k_intersect, k_shade)
 constexpr int kRayBins = 16; // 2^4 reach keys
 constexpr int kMaxBins = 64; // shade-coherence bins (miss, then 2 per entity: entering / exiting); larger scenes shade unbinned
 
