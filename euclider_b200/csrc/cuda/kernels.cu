@@ -9,6 +9,7 @@
 // (src/universe/entity/surface.rs:62-162).  Compiled with -fmad=false.
 #include "pipeline.cuh"
 #include "shade.cuh"
+#include <cstdlib>
 
 namespace eucl {
 
@@ -876,6 +877,24 @@ void launch_trace_path(int dim, const Launch& l, const double* d_in, double dist
 }
 
 cudaError_t configure_kernels(size_t smem_bytes) {
+    // Shared-memory carveout of the two hot kernels: just what their resident CTAs need, the rest of the 256 KB stays
+    // L1 for their local memory (CSG hit lists, spills).  Measured on 3d_room: 19.6 ms with the driver's default split,
+    // 19.3 ms at 25 %, 21.3 ms at 100 %.  A hint only; EUCL_CARVEOUT (percent) overrides.
+    {
+        int dev = 0, max_smem_sm = 228 * 1024;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        const size_t need = (size_t)(kResidentThreads / kBlock) * (smem_bytes + 2048);
+        int pct = (int)((need * 100 + (size_t)max_smem_sm - 1) / (size_t)max_smem_sm);
+        if (const char* c = getenv("EUCL_CARVEOUT")) pct = atoi(c);
+        pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
+        cudaFuncSetAttribute(k_intersect<3>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_intersect<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_shade<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_shade<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_shade<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_shade<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     if (smem_bytes <= 48 * 1024) return cudaSuccess;
     const int v = (int)smem_bytes;
     cudaError_t e;
