@@ -658,7 +658,7 @@ Workspace carve(EuclScene* s, int dim, int cap) {
     ws.bin_count = small + SmallLayout::bins;
     ws.order = (int32_t*)s->order.ptr;
     const bool bin = s->order.ptr != nullptr;
-    ws.n_bins = bin ? 2 * s->n_entities + 1 : 1;
+    ws.n_bins = bin ? kBinsPerEntity * s->n_entities + 1 : 1;
     ws.rbin_count = small + SmallLayout::rbins;
     ws.rorder = (int32_t*)s->rorder.ptr;
     ws.ray_bins = s->rorder.ptr != nullptr && s->ray_bins_now ? 1 : 0;
@@ -701,10 +701,10 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         const bool tree_resolve = env_int("EUCL_TREE_RESOLVE", 0) != 0; // 1: one pointer-chasing kernel instead of the level-by-level k_resolve launches (fewer launches, but 3x slower on glass scenes: measured)
         const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
-        const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && 2 * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
+        const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && kBinsPerEntity * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
         auto workspace_bytes = [&](size_t cap) {
             return arena_bytes(dim, cap) + (want_rorder ? sizeof(int32_t) * (size_t)kRayBins * cap : 0) +
-                   (want_order ? sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * cap : 0);
+                   (want_order ? sizeof(int32_t) * (size_t)(kBinsPerEntity * s->n_entities + 1) * cap : 0);
         };
 
         for (int row0 = 0; row0 < (int)my_rows;) {
@@ -732,7 +732,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     if (!too_big) {
                         cudaError_t e = s->nodes.ensure(arena_bytes(dim, (size_t)want));
                         if (e == cudaSuccess && want_rorder) e = s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want);
-                        if (e == cudaSuccess && want_order) e = s->order.ensure(sizeof(int32_t) * (size_t)(2 * s->n_entities + 1) * (size_t)want);
+                        if (e == cudaSuccess && want_order) e = s->order.ensure(sizeof(int32_t) * (size_t)(kBinsPerEntity * s->n_entities + 1) * (size_t)want);
                         if (e == cudaSuccess) {
                             s->arena_capacity = (int)want;
                         } else { // leave a consistent (empty) workspace behind and try a smaller chunk

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
         valid = valid && ws.ray_cur[node] >= 0;
         int ent = -1;
         bool exiting_flag = false;
+        double cos_hint = 0.0;
         if (valid) {
             Vec<D> o, d, p, n;
             load_ray<D>(ws, node, o, d);
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
             ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, ts, (int)blockDim.x);
             ws.hit_ei[node] = HitInfo{ent, exiting ? 1 : 0, cos_raw};
             exiting_flag = exiting;
+            cos_hint = cos_raw;
             if (ent >= 0) store_hit<D>(ws, node, p, n);
         }
         if (ws.n_bins > 1) {
@@ -319,8 +321,18 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
             // one atomicAdd per (warp, distinct key), ranks from the match mask
             const unsigned active = __ballot_sync(0xffffffffu, valid);
             if (valid) {
-                // key: miss = 0, else 1 + 2 * entity + exiting (exiting hits run material_at, entering ones do not)
-                const int key = ent < 0 ? 0 : 1 + 2 * ent + (exiting_flag ? 1 : 0);
+                // key: miss = 0, else 1 + 3 * entity + class.  Classes: 0 entering, 1 exiting (these run material_at),
+                // 2 exiting a Fresnel surface beyond the critical angle (they only reflect: no Snell rotation, no
+                // material_at).  The class is an ordering hint estimated from cos_raw; shading decides for real.
+                int cls = exiting_flag ? 1 : 0;
+                if (exiting_flag && ent >= 0) {
+                    const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
+                    if (sf.ratio_op == EUCL_RATIO_FRESNEL) {
+                        // (from_index / to_index)^2 sin^2 > 1 with from = ratio_a, to = ratio_b when exiting; no division
+                        if (sf.ratio_a * sf.ratio_a * (1.0 - cos_hint * cos_hint) > sf.ratio_b * sf.ratio_b) cls = 2;
+                    }
+                }
+                const int key = ent < 0 ? 0 : 1 + kBinsPerEntity * ent + cls;
                 const unsigned peers = __match_any_sync(active, key);
                 const int leader = __ffs(peers) - 1;
                 int slot = 0;

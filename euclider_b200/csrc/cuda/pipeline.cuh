@@ -79,7 +79,7 @@ struct Workspace {
     int32_t* level_off; // [EUCL_MAX_LEVELS + 1] first node id of each level
     int32_t* overflow;  // set when a child could not be appended
     int32_t* cam_entity; // material_at(camera location), -1 if none
-    int32_t n_bins;      // 1: shade in node order; else 2 * n_entities + 1 bins keyed by (hit entity, exiting), 0 = miss
+    int32_t n_bins;      // 1: shade in node order; else kBinsPerEntity * n_entities + 1 bins keyed by (hit entity, class), 0 = miss
     int32_t _pad2;
     int32_t* bin_count;  // [EUCL_MAX_LEVELS + 1][kMaxBins] nodes per (level, hit-entity bin)
     int32_t* order;      // [n_bins][capacity] node ids of the current level grouped by bin (reused per level)
@@ -105,7 +105,8 @@ struct Launch {
 constexpr int kBlock = EUCL_BLOCK;          // threads per CTA of the scene-walking kernels
 constexpr int kResidentThreads = 512;       // per SM at 128 registers per thread (k_intersect, k_shade)
 constexpr int kRayBins = 16; // 2^4 reach keys
-constexpr int kMaxBins = 64; // shade-coherence bins (miss, then 2 per entity: entering / exiting); larger scenes shade unbinned
+constexpr int kBinsPerEntity = 3; // entering, exiting, exiting with total internal reflection predicted
+constexpr int kMaxBins = 64; // shade-coherence bins (miss, then kBinsPerEntity per entity); larger scenes shade unbinned
 
 // kernels.cu
 void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws);
