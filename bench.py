@@ -360,11 +360,11 @@ def main():
                     "peak_dfma_tops": dfma.value, "traffic": None, "flops_per_segment": f_scene}
         if args.scene == "3d_room" and (width, height) == (3840, 2160):
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_intersect launch (level 8 of a whole-frame chunk,
-            # 4.15 M rays) from the committed ncu --set full capture (profiles/r1c_ncu_k_intersect_level8.txt).
+            # 4.15 M rays) from the committed ncu --set full capture (profiles/r1d_ncu_k_intersect_level8.txt).
             # Algorithmic bytes of that launch: none beyond its queue records (ray 52 B in, hit 64 B out per ray =
             # 482 MB); the frame itself is 3 B/pixel, written by k_final.
-            roofline["traffic"] = 352.853248e6 + 293.359104e6
-            roofline["traffic_note"] = "one level-8 k_intersect launch, 4.15 M rays, ncu --set full capture (profiles/r1c_*)"
+            roofline["traffic"] = 353.219328e6 + 294.449664e6
+            roofline["traffic_note"] = "one level-8 k_intersect launch, 4.15 M rays, ncu --set full capture (profiles/r1d_*)"
         if prof is not None and prof["ms_intersect"] > 0:
             achieved = prof["segments"] * f_scene / (prof["ms_intersect"] * 1e-3) / 1e12
             roofline.update({"kernel": "k_intersect (all levels of one frame)", "achieved": achieved, "frac": achieved / peak,
