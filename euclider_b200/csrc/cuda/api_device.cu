@@ -693,7 +693,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         if ((long long)width > (1ll << 30)) return fail(EUCL_ERR_INVALID_ARGUMENT, "frame rows too wide");
         EUCL_CUDA(s->small.ensure(sizeof(int32_t) * kSmallInts));
         if (s->arena_factor <= 0.0) s->arena_factor = std::max(1.0, (double)env_int("EUCL_ARENA_FACTOR_X10", 45) / 10.0);
-        // queue kernels run as ONE wave of resident CTAs (4 per SM at 128 registers) walking their level with a grid
+        // queue kernels run as ONE wave of resident CTAs (512 threads per SM at 128 registers) walking their level with a grid
         // stride: measured faster than 2-8 waves on glass scenes (3d_room 20.7 -> 20.0 ms), equal elsewhere
         Launch l{s->stream, s->d_blob, s->smem_bytes,
                  s->sm_count * std::max(1, env_int("EUCL_BLOCKS_PER_SM", kResidentThreads / kBlock)),
