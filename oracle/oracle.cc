@@ -32,6 +32,20 @@
 
 namespace {
 
+// ---------------------------------------------------------------------------------------------
+// ORACLE_COUNT_FLOPS build (liboracle_count.so): counts the floating-point operations of a render so that
+// the work per ray segment can be set against the algorithmic bound of SURVEY.md 8(d) ("F_oracle").
+// Vector arithmetic is counted exactly (every +, -, *, / of the Vec operators and dot); the scalar
+// tails of the primitive intersectors, the membership tests and angle_between add the constants
+// written next to them; one libm call counts as one operation.  Colour arithmetic (palette blends,
+// quantisation) is not counted.  Never used for timing.
+#ifdef ORACLE_COUNT_FLOPS
+static thread_local uint64_t g_flops = 0;
+#define FLOPS(n) (g_flops += (uint64_t)(n))
+#else
+#define FLOPS(n) ((void)0)
+#endif
+
 // Transcendental functions.  The reference calls the platform libm through Rust's std (f64::acos
 // ...).  Two builds of this oracle exist:
 //   liboracle.so      (default)           : the host's glibc -- what the Rust binary would link here
@@ -39,19 +53,19 @@ namespace {
 //                                           path uses, for BIT-EXACT comparison with the GPU
 namespace om {
 #ifdef ORACLE_DETMATH
-inline double acos(double x) { return eucl_det::det_acos(x); }
-inline double asin(double x) { return eucl_det::det_asin(x); }
-inline double sin(double x) { return eucl_det::det_sin(x); }
-inline double cos(double x) { return eucl_det::det_cos(x); }
-inline double atan(double x) { return eucl_det::det_atan(x); }
-inline double atan2(double y, double x) { return eucl_det::det_atan2(y, x); }
+inline double acos(double x) { FLOPS(1); return eucl_det::det_acos(x); }
+inline double asin(double x) { FLOPS(1); return eucl_det::det_asin(x); }
+inline double sin(double x) { FLOPS(1); return eucl_det::det_sin(x); }
+inline double cos(double x) { FLOPS(1); return eucl_det::det_cos(x); }
+inline double atan(double x) { FLOPS(1); return eucl_det::det_atan(x); }
+inline double atan2(double y, double x) { FLOPS(1); return eucl_det::det_atan2(y, x); }
 #else
-inline double acos(double x) { return std::acos(x); }
-inline double asin(double x) { return std::asin(x); }
-inline double sin(double x) { return std::sin(x); }
-inline double cos(double x) { return std::cos(x); }
-inline double atan(double x) { return std::atan(x); }
-inline double atan2(double y, double x) { return std::atan2(y, x); }
+inline double acos(double x) { FLOPS(1); return std::acos(x); }
+inline double asin(double x) { FLOPS(1); return std::asin(x); }
+inline double sin(double x) { FLOPS(1); return std::sin(x); }
+inline double cos(double x) { FLOPS(1); return std::cos(x); }
+inline double atan(double x) { FLOPS(1); return std::atan(x); }
+inline double atan2(double y, double x) { FLOPS(1); return std::atan2(y, x); }
 #endif
 } // namespace om
 
@@ -77,12 +91,14 @@ Vec<D> load(const double* p) {
 template <int D>
 Vec<D> operator+(const Vec<D>& a, const Vec<D>& b) {
     Vec<D> r;
+    FLOPS(D);
     for (int k = 0; k < D; ++k) r[k] = a[k] + b[k];
     return r;
 }
 template <int D>
 Vec<D> operator-(const Vec<D>& a, const Vec<D>& b) {
     Vec<D> r;
+    FLOPS(D);
     for (int k = 0; k < D; ++k) r[k] = a[k] - b[k];
     return r;
 }
@@ -95,17 +111,20 @@ Vec<D> operator-(const Vec<D>& a) {
 template <int D>
 Vec<D> operator*(const Vec<D>& a, double s) {
     Vec<D> r;
+    FLOPS(D);
     for (int k = 0; k < D; ++k) r[k] = a[k] * s;
     return r;
 }
 template <int D>
 Vec<D> operator/(const Vec<D>& a, double s) {
     Vec<D> r;
+    FLOPS(D);
     for (int k = 0; k < D; ++k) r[k] = a[k] / s;
     return r;
 }
 template <int D>
 double dot(const Vec<D>& a, const Vec<D>& b) {
+    FLOPS(2 * D - 1);
     double s = a[0] * b[0];
     for (int k = 1; k < D; ++k) s = s + a[k] * b[k];
     return s;
@@ -113,13 +132,17 @@ double dot(const Vec<D>& a, const Vec<D>& b) {
 template <int D>
 double norm_squared(const Vec<D>& a) { return dot(a, a); }
 template <int D>
-double norm(const Vec<D>& a) { return std::sqrt(norm_squared(a)); }
+double norm(const Vec<D>& a) {
+    FLOPS(1);
+    return std::sqrt(norm_squared(a));
+}
 template <int D>
 Vec<D> normalize(const Vec<D>& a) { return a / norm(a); }
 
 // util.rs:712-722
 template <int D>
 double angle_between(const Vec<D>& a, const Vec<D>& b) {
+    FLOPS(2); // *, / (the acos counts itself)
     double result = om::acos(dot(a, b) / (norm(a) * norm(b)));
     return std::isnan(result) ? 0.0 : result;
 }
@@ -368,7 +391,9 @@ int intersect_prim(const EuclPrim& pr, const Vec<D>& location, const Vec<D>& dir
         double b = 2.0 * dot(direction, rel);
         double c = norm_squared(rel) - radius * radius;
         double d = b * b - 4.0 * a * c;
+        FLOPS(7); // reject stage, scalar part
         if (d < 0.0) return 0;
+        FLOPS(9); // sqrt, two roots
         double d_sqrt = std::sqrt(d);
         double t1 = (-b - d_sqrt) / (2.0 * a);
         double t2 = (-b + d_sqrt) / (2.0 * a);
@@ -399,6 +424,7 @@ int intersect_prim(const EuclPrim& pr, const Vec<D>& location, const Vec<D>& dir
     case EUCL_PRIM_HALFSPACE: { // shape.rs:779-809, 843-870
         Vec<D> n = load<D>(pr.v0);
         double t = -(dot(n, location) + pr.s0) / dot(n, direction);
+        FLOPS(3);
         if (t < 0.0) return 0; // NaN and +inf pass, as in the reference
         out[0].location = direction * t + location;
         out[0].normal = n;
@@ -416,7 +442,9 @@ int intersect_prim(const EuclPrim& pr, const Vec<D>& location, const Vec<D>& dir
         double b = (1.0 + 1.0) * dot(a_vec, c_vec);
         double c = norm_squared(c_vec) - radius * radius;
         double d = b * b - 4.0 * a * c;
+        FLOPS(7);
         if (d < 0.0) return 0;
+        FLOPS(9);
         double d_sqrt = std::sqrt(d);
         double t1 = (-b - d_sqrt) / (2.0 * a);
         double t2 = (-b + d_sqrt) / (2.0 * a);
@@ -457,16 +485,19 @@ bool prim_inside(const EuclPrim& pr, const Vec<D>& point) {
     case EUCL_PRIM_VOID: return true;       // shape.rs:614-619
     case EUCL_PRIM_SPHERE: {                // shape.rs:734-738
         Vec<D> center = load<D>(pr.v0);
+        FLOPS(1);
         return norm_squared(center - point) <= pr.s0 * pr.s0;
     }
     case EUCL_PRIM_HYPERPLANE: return false; // shape.rs:812-817
     case EUCL_PRIM_HALFSPACE: {              // shape.rs:873-881
+        FLOPS(1);
         double result = dot(load<D>(pr.v0), point) + pr.s0;
         return pr.s1 == rust_signum(result);
     }
     case EUCL_PRIM_CYLINDER: { // shape.rs:1030-1038
         Vec<D> center = load<D>(pr.v0), axis = load<D>(pr.v1);
         Vec<D> on_axis = axis * dot(axis, point - center) + center;
+        FLOPS(1);
         return norm_squared(point - on_axis) <= pr.s0 * pr.s0;
     }
     }
@@ -1193,7 +1224,17 @@ int render_impl(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t w
     std::vector<Tracer<D>> tracers;
     tracers.reserve((size_t)threads);
     for (int t = 0; t < threads; ++t) tracers.emplace_back(*scene, *camera, time);
+#ifdef ORACLE_COUNT_FLOPS
+    std::atomic<uint64_t> flops_total{0};
+#endif
     auto work = [&](int t) {
+#ifdef ORACLE_COUNT_FLOPS
+        g_flops = 0;
+        struct Flush {
+            std::atomic<uint64_t>& total;
+            ~Flush() { total += g_flops; }
+        } flush{flops_total};
+#endif
         Tracer<D>& tr = tracers[(size_t)t];
         for (;;) {
             const uint64_t begin = next_tile.fetch_add(tile);
@@ -1210,7 +1251,7 @@ int render_impl(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t w
     work(0);
     for (auto& th : pool) th.join();
     if (stats) {
-        // stats[0] = segments, [1] = nodes, [2..5] = undefined-corner counters, [8 + l] = level l
+        // stats[0] = segments, [1] = nodes, [2..5] = undefined-corner counters, [6] = counted flops (counting build), [8 + l] = level l
         std::memset(stats, 0, sizeof(uint64_t) * (8 + EUCL_MAX_LEVELS));
         for (auto& tr : tracers) {
             for (uint32_t l = 0; l <= camera->max_depth && l < EUCL_MAX_LEVELS; ++l) {
@@ -1223,6 +1264,9 @@ int render_impl(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t w
             stats[4] += tr.counters.no_material;
             stats[5] += tr.counters.csg_runaway;
         }
+#ifdef ORACLE_COUNT_FLOPS
+        stats[6] = flops_total.load(); // counted floating-point operations of this call (see FLOPS)
+#endif
     }
     return 0;
 }

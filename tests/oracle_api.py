@@ -15,14 +15,15 @@ from euclider_b200._capi import EUCL_MAX_LEVELS, EuclCamera, EuclFlatScene, Eucl
 
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
-LIB_PATHS = {"glibc": ORACLE_DIR / "liboracle.so", "det": ORACLE_DIR / "liboracle_det.so"}
+LIB_PATHS = {"glibc": ORACLE_DIR / "liboracle.so", "det": ORACLE_DIR / "liboracle_det.so",
+             "count": ORACLE_DIR / "liboracle_count.so"}  # "count": det + flop counters (tools/oracle_flops.py)
 _libs = {}
 
 dptr = C.POINTER(C.c_double)
 
 
-def build() -> None:
-    subprocess.run(["make", "-C", str(ORACLE_DIR), "all"], check=True, capture_output=True)
+def build(target: str = "all") -> None:
+    subprocess.run(["make", "-C", str(ORACLE_DIR), target], check=True, capture_output=True)
 
 
 def lib(variant: str = "det") -> C.CDLL:
@@ -32,7 +33,7 @@ def lib(variant: str = "det") -> C.CDLL:
         path = LIB_PATHS[variant]
         deps = [ORACLE_DIR / "oracle.cc", ROOT / "include" / "euclider_b200.h", ROOT / "include" / "eucl_detmath.h"]
         if not path.exists() or path.stat().st_mtime < max(d.stat().st_mtime for d in deps):
-            build()
+            build("liboracle_count.so" if variant == "count" else "all")
         h = C.CDLL(str(path))
         h.oracle_render.restype = C.c_int
         h.oracle_render.argtypes = [C.POINTER(EuclFlatScene), C.POINTER(EuclCamera), C.c_uint32, C.c_uint32, C.c_double,
@@ -110,7 +111,7 @@ def render(env, width: int, height: int, time: float = 0.0, threads: int | None 
     levels = int(cam.max_depth) + 1
     return rgb, hit, {
         "segments": int(stats[0]), "nodes": int(stats[1]), "nan_channel": int(stats[2]), "bad_texcoord": int(stats[3]),
-        "no_material": int(stats[4]), "csg_runaway": int(stats[5]),
+        "no_material": int(stats[4]), "csg_runaway": int(stats[5]), "flops": int(stats[6]),
         "level_counts": [int(v) for v in stats[8:8 + levels]],
     }
 
