@@ -156,10 +156,24 @@ def run_reference(args, width, height):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_OUT = sys.stdout
+
+
+def emit(obj) -> None:
+    """The result lines go to the process's ORIGINAL stdout (see main)."""
+    print(json.dumps(obj), file=_RESULT_OUT, flush=True)
 
 
 def main():
+    # stdout carries the JSON result lines and nothing else: libraries that write to file descriptor 1 on their own
+    # (NCCL prints "NCCL version ..." there) are sent to stderr instead
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -394,7 +408,7 @@ def main():
             "fps": 1e3 / ms_per_step, "e2e": e2e, "gpu_launches": launches, "retries": retries, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1 and args.check:
         step()
         sync_all()
@@ -403,7 +417,7 @@ def main():
             env.set_stream(0, device=local_rank)
             whole = env.render((width, height), args.time, device=local_rank)
             same = bool(np.array_equal(whole.data, host.numpy()))
-            print(json.dumps({"check": "gathered frame == single-GPU frame", "equal": same}), flush=True)
+            emit({"check": "gathered frame == single-GPU frame", "equal": same})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

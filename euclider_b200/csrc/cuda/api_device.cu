@@ -84,7 +84,8 @@ struct EuclScene {
     int ray_bins_mode = -1;      // -1 undecided, 0 off, 1 on
     bool ray_bins_now = true;    // setting of the frame being rendered
     float tune_ms[2] = {0.f, 0.f};
-    int warm_frames = 0;
+    uint64_t tune_pixels = 0;    // frame size the two timings belong to
+    int warm_frames = 0;         // frames rendered so far
     int n_entities = 0;
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
@@ -866,11 +867,16 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     if (s->ray_bins_mode < 0 && st.retries == 0 && my_rows > 0 && o->pipeline == EUCL_PIPELINE_WAVEFRONT) {
         if (s->n_cull == 0) {
             s->ray_bins_mode = 0;
-        } else if (s->warm_frames++ >= 1) { // skip the very first frame (allocations, cold caches)
+        } else if (s->warm_frames >= 1) { // never the scene's very first frame (allocations, cold caches)
+            if (s->tune_pixels != st.pixels) { // only frames of one size are comparable
+                s->tune_pixels = st.pixels;
+                s->tune_ms[0] = s->tune_ms[1] = 0.f;
+            }
             s->tune_ms[s->ray_bins_now ? 1 : 0] = st.ms_total;
             if (s->tune_ms[0] > 0.f && s->tune_ms[1] > 0.f) s->ray_bins_mode = s->tune_ms[1] < s->tune_ms[0] ? 1 : 0;
         }
     }
+    s->warm_frames++;
     if (stats) *stats = st;
     return EUCL_OK;
 }
