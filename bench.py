@@ -394,7 +394,6 @@ def main():
                 cpu = {"value": c_segs / c_secs / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}
             except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU number
                 cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
-        arena_mb = None
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
