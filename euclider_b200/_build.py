@@ -37,7 +37,7 @@ def _sources():
 
 def _stamp(paths) -> str:
     h = hashlib.sha256()
-    deps = list(paths) + sorted(CSRC.rglob("*.h")) + sorted(CSRC.rglob("*.cuh")) + [ROOT / "include" / "euclider_b200.h"]
+    deps = list(paths) + sorted(CSRC.rglob("*.h")) + sorted(CSRC.rglob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
     for p in deps:
         h.update(str(p).encode())
         h.update(p.read_bytes())

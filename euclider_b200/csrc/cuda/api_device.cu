@@ -6,6 +6,7 @@
 // entry point fails with EUCL_ERR_NO_DEVICE / EUCL_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -111,35 +112,154 @@ static_assert(SmallLayout::total <= kSmallInts, "small buffer layout");
 
 size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
-// Structural validation of the post-order CSG programs of a flat scene.
-int validate_programs(const EuclFlatScene& f, std::string* why) {
+// Validation of a caller-built flat scene: every cross-table index, opcode and program that the
+// device code dereferences without checks.  EUCL_ERR_INVALID_ARGUMENT for malformed tables,
+// EUCL_ERR_SCENE_LIMIT for well-formed programs that exceed a fixed device stack (shade.cuh:
+// kExprStackMax, kColorStackMax).
+int validate_scene(const EuclFlatScene& f, std::string* why) {
+    auto bad = [&](const std::string& msg) {
+        *why = msg;
+        return (int)EUCL_ERR_INVALID_ARGUMENT;
+    };
+    const int counts[] = {f.n_prims, f.n_nodes, f.n_entities, f.n_materials, f.n_transforms, f.n_expr_ops,
+                          f.n_surfaces, f.n_color_ops, f.n_mapped_textures, f.n_textures};
+    for (int c : counts)
+        if (c < 0) return bad("negative table size");
+    if ((f.n_prims && !f.prims) || (f.n_nodes && !f.nodes) || (f.n_entities && !f.entities) || (f.n_materials && !f.materials) ||
+        (f.n_transforms && !f.transforms) || (f.n_expr_ops && !f.expr_ops) || (f.n_surfaces && !f.surfaces) ||
+        (f.n_color_ops && !f.color_ops) || (f.n_mapped_textures && !f.mapped_textures) || (f.n_textures && !f.textures))
+        return bad("null table with a non-zero size");
+    for (int i = 0; i < f.n_prims; ++i)
+        if (f.prims[i].kind < EUCL_PRIM_VOID || f.prims[i].kind > EUCL_PRIM_CYLINDER)
+            return bad("primitive " + std::to_string(i) + ": unknown kind");
     for (int e = 0; e < f.n_entities; ++e) {
         const EuclEntity& ent = f.entities[e];
-        if (ent.node_first < 0 || ent.node_root >= f.n_nodes || ent.node_first > ent.node_root) {
-            *why = "entity " + std::to_string(e) + ": node range out of bounds";
-            return EUCL_ERR_INVALID_ARGUMENT;
-        }
+        if (ent.node_first < 0 || ent.node_root >= f.n_nodes || ent.node_first > ent.node_root)
+            return bad("entity " + std::to_string(e) + ": node range out of bounds");
+        if (ent.material < 0 || ent.material >= f.n_materials) return bad("entity " + std::to_string(e) + ": material index out of bounds");
+        if (ent.surface < -1 || ent.surface >= f.n_surfaces) return bad("entity " + std::to_string(e) + ": surface index out of bounds");
         int depth = 0;
         for (int n = ent.node_first; n <= ent.node_root; ++n) {
             const EuclNode& nd = f.nodes[n];
             if (nd.op == EUCL_CSG_LEAF) {
-                if (nd.prim < 0 || nd.prim >= f.n_prims) {
-                    *why = "node " + std::to_string(n) + ": primitive index out of bounds";
-                    return EUCL_ERR_INVALID_ARGUMENT;
-                }
+                if (nd.prim < 0 || nd.prim >= f.n_prims) return bad("node " + std::to_string(n) + ": primitive index out of bounds");
                 ++depth;
             } else {
-                if (nd.op < EUCL_CSG_UNION || nd.op > EUCL_CSG_SYMDIFF || depth < 2 || nd.first < ent.node_first ||
-                    nd.first >= n) {
-                    *why = "node " + std::to_string(n) + ": malformed post-order program";
-                    return EUCL_ERR_INVALID_ARGUMENT;
-                }
+                if (nd.op < EUCL_CSG_UNION || nd.op > EUCL_CSG_SYMDIFF || depth < 2 || nd.first < ent.node_first || nd.first >= n)
+                    return bad("node " + std::to_string(n) + ": malformed post-order program");
                 --depth;
             }
         }
-        if (depth != 1) {
-            *why = "entity " + std::to_string(e) + ": CSG program does not reduce to one shape";
-            return EUCL_ERR_INVALID_ARGUMENT;
+        if (depth != 1) return bad("entity " + std::to_string(e) + ": CSG program does not reduce to one shape");
+    }
+    // expression programs: operand counts and the peak depth of the device's evaluation stack
+    auto check_expr = [&](int first, int len, const std::string& what, int* status) {
+        if (first < 0 || len < 0 || (long long)first + len > f.n_expr_ops) {
+            *status = bad(what + ": expression range out of bounds");
+            return;
+        }
+        int sp = 0, peak = 0;
+        for (int i = first; i < first + len; ++i) {
+            const EuclExprOp& o = f.expr_ops[i];
+            int pops = 0;
+            switch (o.op) {
+            case EUCL_EX_CONST: break;
+            case EUCL_EX_VAR:
+                if (o.arg < 0 || o.arg >= f.dim) {
+                    *status = bad(what + ": variable index out of range");
+                    return;
+                }
+                break;
+            case EUCL_EX_NEG: pops = 1; break;
+            case EUCL_EX_FUNC1:
+                if (o.arg < EUCL_FN_SQRT || o.arg > EUCL_FN_SIGNUM) {
+                    *status = bad(what + ": unknown unary function");
+                    return;
+                }
+                pops = 1;
+                break;
+            case EUCL_EX_FUNC2:
+                if (o.arg < EUCL_FN_ATAN2 || o.arg > EUCL_FN_MIN) {
+                    *status = bad(what + ": unknown binary function");
+                    return;
+                }
+                pops = 2;
+                break;
+            case EUCL_EX_ADD: case EUCL_EX_SUB: case EUCL_EX_MUL: case EUCL_EX_DIV: case EUCL_EX_REM: case EUCL_EX_POW:
+                pops = 2;
+                break;
+            default: *status = bad(what + ": unknown expression opcode"); return;
+            }
+            if (sp < pops) {
+                *status = bad(what + ": expression stack underflow");
+                return;
+            }
+            sp = sp - pops + 1;
+            peak = std::max(peak, sp);
+        }
+        if (len > 0 && sp != 1) {
+            *status = bad(what + ": expression does not reduce to one value");
+            return;
+        }
+        if (peak > kExprStackMax) {
+            *why = what + ": expression needs " + std::to_string(peak) + " stack slots, the device evaluator has " +
+                   std::to_string(kExprStackMax);
+            *status = EUCL_ERR_SCENE_LIMIT;
+        }
+    };
+    for (int m = 0; m < f.n_materials; ++m) {
+        const EuclMaterial& mat = f.materials[m];
+        if (mat.kind != EUCL_MAT_VACUUM && mat.kind != EUCL_MAT_LINEAR_SPACE) return bad("material " + std::to_string(m) + ": unknown kind");
+        if (mat.kind == EUCL_MAT_LINEAR_SPACE &&
+            (mat.transform_first < 0 || mat.n_transforms < 0 || (long long)mat.transform_first + mat.n_transforms > f.n_transforms))
+            return bad("material " + std::to_string(m) + ": transformation range out of bounds");
+    }
+    for (int t = 0; t < f.n_transforms; ++t)
+        for (int k = 0; k < f.dim; ++k) {
+            int status = EUCL_OK;
+            check_expr(f.transforms[t].fwd_first[k], f.transforms[t].fwd_len[k], "transformation " + std::to_string(t), &status);
+            if (status == EUCL_OK)
+                check_expr(f.transforms[t].inv_first[k], f.transforms[t].inv_len[k], "transformation " + std::to_string(t) + " (inverse)", &status);
+            if (status != EUCL_OK) return status;
+        }
+    auto mapped_ok = [&](int mt) {
+        return mt >= 0 && mt < f.n_mapped_textures;
+    };
+    for (int m = 0; m < f.n_mapped_textures; ++m) {
+        const EuclMappedTexture& mt = f.mapped_textures[m];
+        if (mt.texture < 0 || mt.texture >= f.n_textures) return bad("mapped texture " + std::to_string(m) + ": texture index out of bounds");
+        if (mt.filter != EUCL_TEX_NEAREST && mt.filter != EUCL_TEX_LINEAR) return bad("mapped texture " + std::to_string(m) + ": unknown filter");
+        if (mt.uv_kind != EUCL_UV_SPHERE3) return bad("mapped texture " + std::to_string(m) + ": unknown uv mapping");
+    }
+    if (f.background < -1 || f.background >= f.n_mapped_textures) return bad("background: mapped texture index out of bounds");
+    for (int sidx = 0; sidx < f.n_surfaces; ++sidx) {
+        const EuclSurface& sf = f.surfaces[sidx];
+        const std::string what = "surface " + std::to_string(sidx);
+        if (sf.ratio_op != EUCL_RATIO_UNIFORM && sf.ratio_op != EUCL_RATIO_FRESNEL) return bad(what + ": unknown reflection ratio provider");
+        if (sf.refl_op != EUCL_REFL_SPECULAR) return bad(what + ": unknown reflection direction provider");
+        if (sf.thr_op != EUCL_THR_IDENTITY && sf.thr_op != EUCL_THR_SNELL) return bad(what + ": unknown threshold direction provider");
+        if (sf.color_first < 0 || sf.color_len < 0 || (long long)sf.color_first + sf.color_len > f.n_color_ops)
+            return bad(what + ": colour program out of bounds");
+        int sp = 0, peak = 0;
+        for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
+            const EuclColorOp& op = f.color_ops[i];
+            if (op.op < EUCL_COL_UNIFORM || op.op > EUCL_COL_BLEND) return bad(what + ": unknown colour opcode");
+            if (op.op == EUCL_COL_TEXTURE && op.i0 != -1 && !mapped_ok(op.i0)) return bad(what + ": mapped texture index out of bounds");
+            if (op.op == EUCL_COL_PERLIN_HUE && f.dim != 3) return bad(what + ": perlin_hue is a 3-D provider");
+            if (op.op == EUCL_COL_BLEND) {
+                if (op.i0 < EUCL_BLEND_RATIO || op.i0 > EUCL_BLEND_EXCLUSION) return bad(what + ": unknown blend function");
+                if (sp < 2) return bad(what + ": colour stack underflow");
+                sp -= 1;
+            } else {
+                sp += 1;
+            }
+            peak = std::max(peak, sp);
+        }
+        if (sf.color_len > 0 && sp != 1) return bad(what + ": colour program does not reduce to one colour");
+        if (peak > kColorStackMax) {
+            *why = what + ": colour program nests " + std::to_string(peak) + " deep, the device evaluator has " +
+                   std::to_string(kColorStackMax) + " slots";
+            return EUCL_ERR_SCENE_LIMIT;
         }
     }
     return EUCL_OK;
@@ -427,15 +547,16 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     if (!flat || !out) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: null argument");
     *out = nullptr;
     if (flat->dim != 3 && flat->dim != 4) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: dim must be 3 or 4");
-    const int n_dev = eucl_device_count();
-    if (n_dev <= 0) return fail(EUCL_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
-    if (device < 0 || device >= n_dev) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: device index out of range");
+    // the scene is validated before any device is touched (also without one: tests/test_scene_limits.py)
+    std::string why;
+    int status = validate_scene(*flat, &why);
+    if (status != EUCL_OK) return fail(status, why);
     for (int t = 0; t < flat->n_textures; ++t)
         if (flat->textures[t].width == 0 || flat->textures[t].height == 0 || !flat->texels)
             return fail(EUCL_ERR_TEXTURE_MISSING, "texture slot " + std::to_string(t) + " was never filled");
-    std::string why;
-    int status = validate_programs(*flat, &why);
-    if (status != EUCL_OK) return fail(status, why);
+    const int n_dev = eucl_device_count();
+    if (n_dev <= 0) return fail(EUCL_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: device index out of range");
 
     EUCL_CUDA(cudaSetDevice(device));
     EuclScene* s = new EuclScene();
@@ -667,8 +788,7 @@ Workspace carve(EuclScene* s, int dim, int cap) {
 }
 
 int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* d_rgb, int32_t* d_hit,
-                EuclStats* stats, bool sync_and_time) {
-    (void)sync_and_time;
+                EuclStats* stats) {
     const int dim = s->dim;
     FrameParams fp;
     frame_params(*cam, *o, &fp);
@@ -699,7 +819,6 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         Launch l{s->stream, s->d_blob, s->smem_bytes,
                  s->sm_count * std::max(1, env_int("EUCL_BLOCKS_PER_SM", kResidentThreads / kBlock)),
                  s->sm_count * std::max(1, env_int("EUCL_MEM_BLOCKS_PER_SM", 8))};
-        const bool tree_resolve = env_int("EUCL_TREE_RESOLVE", 0) != 0; // 1: one pointer-chasing kernel instead of the level-by-level k_resolve launches (fewer launches, but 3x slower on glass scenes: measured)
         const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
         const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && kBinsPerEntity * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
@@ -807,20 +926,15 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
                     dbg("k_shade", (int)cam->max_depth);
                     mark(2);
-                    if (tree_resolve) {
-                        launch_final_tree(l, fp, cp, ws, d_rgb);
-                        dbg("k_final_tree", 0);
-                    } else {
-                        for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
-                            launch_resolve(dim, l, ws, level);
-                            dbg("k_resolve", level);
-                        }
-                        launch_final(dim, l, fp, cp, ws, d_rgb);
-                        dbg("k_final", 0);
+                    for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
+                        launch_resolve(dim, l, ws, level);
+                        dbg("k_resolve", level);
                     }
+                    launch_final(dim, l, fp, cp, ws, d_rgb);
+                    dbg("k_final", 0);
                     mark(3);
                     if (!fault.empty()) return fail(EUCL_ERR_CUDA, "EUCL_DEBUG_SYNC: " + fault);
-                    st.launches += 3 + 2 * cam->max_depth + (tree_resolve || cam->max_depth == 0 ? 0 : cam->max_depth - 1);
+                    st.launches += 3 + 2 * cam->max_depth + (cam->max_depth == 0 ? 0 : cam->max_depth - 1);
                 }
                 EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
                                           s->stream));
@@ -832,6 +946,20 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     float* slot = prof_family[k] == 0 ? &st.ms_raygen : prof_family[k] == 1 ? &st.ms_intersect
                                   : prof_family[k] == 2 ? &st.ms_shade : &st.ms_resolve;
                     *slot += ms;
+                }
+                if (env_int("EUCL_DUMP_LEVELS", 0) && !s->h_small[SmallLayout::overflow]) { // diagnostics: per-level counts, bins, launch times
+                    for (uint32_t lv = 0; lv <= cam->max_depth; ++lv) {
+                        fprintf(stderr, "level %2u count %9d | bins", lv, s->h_small[SmallLayout::count + lv]);
+                        for (int b = 0; b < ws.n_bins && ws.n_bins > 1; ++b) fprintf(stderr, " %d", s->h_small[SmallLayout::bins + lv * kMaxBins + b]);
+                        fprintf(stderr, " | rbins");
+                        for (int b = 0; b < kRayBins; ++b) fprintf(stderr, " %d", s->h_small[SmallLayout::rbins + lv * kRayBins + b]);
+                        fprintf(stderr, "\n");
+                    }
+                    for (size_t k = 1; k < prof_family.size(); ++k) {
+                        float ms = 0.f;
+                        cudaEventElapsedTime(&ms, s->prof_events[k - 1], s->prof_events[k]);
+                        fprintf(stderr, "launch %2zu family %d %.3f ms\n", k, prof_family[k], ms);
+                    }
                 }
                 if (s->h_small[SmallLayout::overflow] == 2)
                     return fail(EUCL_ERR_CUDA, "internal error: a queue index list and its level count disagree");
@@ -886,7 +1014,7 @@ int check_args(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o) {
     if (cam->dim != s->dim) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: camera dimension does not match the scene");
     if (o->width == 0 || o->height == 0 || o->width > (1u << 20) || o->height > (1u << 20))
         return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: bad frame size");
-    if (cam->max_depth + 1 > EUCL_MAX_LEVELS) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: max_depth too large");
+    if (cam->max_depth >= EUCL_MAX_LEVELS) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: max_depth too large");
     if (o->band_world > 1 && o->band_rank >= o->band_world) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: band_rank >= band_world");
     if (o->pipeline != EUCL_PIPELINE_WAVEFRONT && o->pipeline != EUCL_PIPELINE_MEGAKERNEL)
         return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: unknown pipeline");
@@ -903,7 +1031,7 @@ int eucl_render_device(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts
     if (st != EUCL_OK) return st;
     if (!d_out_rgb8) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render_device: null output");
     EUCL_CUDA(cudaSetDevice(s->device));
-    return render_impl(s, cam, o, (uint8_t*)d_out_rgb8, o->want_hit_ids ? (int32_t*)d_out_hit_ids : nullptr, stats, true);
+    return render_impl(s, cam, o, (uint8_t*)d_out_rgb8, o->want_hit_ids ? (int32_t*)d_out_hit_ids : nullptr, stats);
 }
 
 int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* out_rgb8, int32_t* out_hit_ids,
@@ -924,7 +1052,7 @@ int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     }
     EuclRenderOpts opts = *o;
     opts.want_hit_ids = want_hit ? 1 : 0;
-    st = render_impl(s, cam, &opts, (uint8_t*)s->frame.ptr, want_hit ? (int32_t*)s->hit_ids.ptr : nullptr, stats, true);
+    st = render_impl(s, cam, &opts, (uint8_t*)s->frame.ptr, want_hit ? (int32_t*)s->hit_ids.ptr : nullptr, stats);
     if (st != EUCL_OK) return st;
     EUCL_CUDA(cudaMemcpyAsync(out_rgb8, s->frame.ptr, pixels * 3, cudaMemcpyDeviceToHost, s->stream));
     if (want_hit) EUCL_CUDA(cudaMemcpyAsync(out_hit_ids, s->hit_ids.ptr, pixels * 4, cudaMemcpyDeviceToHost, s->stream));

@@ -531,88 +531,6 @@ __global__ void __launch_bounds__(256) k_final(FrameParams fp, ChunkParams cp, W
     }
 }
 
-// K4+K5 fused: one thread resolves the whole ray tree of its pixel depth-first from the node
-// records (children first: transmitted, then reflected), then composites and packs.  Replaces the
-// level-by-level k_resolve launches: inner-node colours stay in registers instead of making a round
-// trip through HBM, and one launch replaces max_depth of them.  Same arithmetic as k_resolve.
-template <int kDepth>
-__global__ void __launch_bounds__(256) k_final_tree(FrameParams fp, ChunkParams cp, Workspace ws,
-                                                    uint8_t* __restrict__ out_rgb8) {
-    if (*ws.overflow) return;
-    struct Frame {
-        double ratio;
-        Rgba t;
-        int rchild;
-        unsigned q;
-        unsigned state; // bit 0: waiting for the reflected child; bit 1: have T
-    };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
-        Frame stack[kDepth];
-        int sp = 0, cur = i;
-        Rgba val{0.0, 0.0, 0.0, 0.0};
-        const unsigned root_flags = ws.meta[i].flags;
-        for (;;) {
-            // ---- descend
-            const NodeMeta m = ws.meta[cur];
-            bool leaf = true;
-            if (m.flags & NODE_LEAF) {
-                val = load_res(ws, cur);
-            } else {
-                Frame f;
-                f.ratio = m.ratio;
-                f.q = m.q;
-                f.rchild = m.rchild;
-                f.state = 0u;
-                f.t = Rgba{0.0, 0.0, 0.0, 0.0};
-                int next = -1;
-                if (m.flags & NODE_HAS_SC) {
-                    f.t = load_res(ws, cur);
-                    f.state = 2u | 1u; // T known; only the reflected child (if any) is pending
-                    next = m.rchild;
-                } else if (m.tchild >= 0) {
-                    next = m.tchild;
-                } else {
-                    f.state = 1u;
-                    next = m.rchild;
-                }
-                if (next >= 0 && sp < kDepth) {
-                    stack[sp++] = f;
-                    cur = next;
-                    leaf = false;
-                } else {
-                    val = f.t; // no child at all (cannot happen for a non-leaf; kept total)
-                }
-            }
-            if (!leaf) continue;
-            // ---- ascend
-            bool done = false;
-            for (;;) {
-                if (sp == 0) {
-                    done = true;
-                    break;
-                }
-                Frame& f = stack[sp - 1];
-                if (!(f.state & 1u)) { // the transmitted child returned
-                    f.t = transmit_over(f.q, val);
-                    f.state |= 2u | 1u;
-                    if (f.rchild >= 0) {
-                        cur = f.rchild;
-                        break;
-                    }
-                    val = f.t;
-                } else { // the reflected child returned
-                    val = (f.state & 2u) ? combine_palette_color(val, f.t, f.ratio) : val;
-                }
-                --sp;
-            }
-            if (done) break;
-        }
-        const int local_row = cp.local_row0 + i / fp.width;
-        const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
-        final_rgb8(val, !(root_flags & NODE_FINAL_RGB), out_rgb8 + ((size_t)orow * fp.width + i % fp.width) * 3);
-    }
-}
-
 // Cross-check pipeline: one thread walks the whole ray tree of its pixel depth-first with an
 // explicit stack (transmitted subtree first, then the reflected one, as the reference recurses).
 constexpr int kMegaMaxDepth = 24;
@@ -869,11 +787,6 @@ void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkPa
                   uint8_t* out_rgb8) {
     (void)dim;
     k_final<<<grid_for(cp.n_pixels, 256, l.grid_mem), 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
-}
-void launch_final_tree(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, uint8_t* out_rgb8) {
-    const int grid = grid_for(cp.n_pixels, 256, l.grid_mem);
-    if (fp.max_depth < 16) k_final_tree<16><<<grid, 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
-    else k_final_tree<EUCL_MAX_LEVELS><<<grid, 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
 }
 void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                        uint8_t* out_rgb8, int32_t* hit_ids_out) {

@@ -118,7 +118,6 @@ void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkPa
 void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level);
 void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                   uint8_t* out_rgb8);
-void launch_final_tree(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, uint8_t* out_rgb8);
 void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                        uint8_t* out_rgb8, int32_t* hit_ids_out);
 void launch_trace_path(int dim, const Launch& l, const double* d_in, double distance, double* d_out, int* d_found);

@@ -79,6 +79,9 @@ struct SceneView {
 #undef EUCL_TABLE
 #endif
 };
+// fixed device evaluation stacks; eucl_scene_create rejects programs that need more (EUCL_ERR_SCENE_LIMIT)
+constexpr int kExprStackMax = 16;  // shade.cuh: eval_expr
+constexpr int kColorStackMax = 8;  // shade.cuh: surface_color
 constexpr int kPlaneStride = 6; // doubles per record of the AoS primitive table (48 B, 16-byte aligned)
 
 #if defined(__CUDACC__)

@@ -255,7 +255,7 @@ __device__ __noinline__ Rgba mapped_color(const SceneView& sv, int mapped, const
 
 // meval-style RPN program (compiled on the host from the scene's expression strings)
 __device__ __noinline__ double eval_expr(const SceneView& sv, int first, int len, const double* vars) {
-    double st[16];
+    double st[kExprStackMax];
     int sp = 0;
     for (int i = first; i < first + len; ++i) {
         const EuclExprOp o = sv.expr_ops()[i];
@@ -335,11 +335,6 @@ __device__ __forceinline__ void material_exit(const SceneView& sv, int entity, V
 }
 
 // --- surface providers -------------------------------------------------------------------------
-
-struct HitContext { // the fields of TracingContext (shape.rs:111-123) the providers read
-    int hit_entity;
-    bool exiting;
-};
 
 // util.rs:631-666: rotate `v` in the plane spanned by (self_, other) by `angle`
 template <int D>
@@ -486,7 +481,7 @@ __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, con
 template <int D>
 __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& location,
                                      const Vec<D>& normal_raw, double cos_raw, double cos_closer, double time_millis) {
-    Rgba stack[8];
+    Rgba stack[kColorStackMax];
     int sp = 0;
     for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
         const EuclColorOp& op = sv.color_ops()[i];

@@ -164,19 +164,11 @@ def test_device_buffer_entry_point(built_lib):
 
 def test_errors_are_statuses_not_aborts(built_lib):
     env = load("3d_fresnel")
-    env.camera.max_depth = 100
-    with pytest.raises(eb.EuclError) as err:
-        env.render((8, 8))
-    assert err.value.status == -1
-
-
-def test_tree_resolve_variant_is_identical(built_lib, monkeypatch):
-    """EUCL_TREE_RESOLVE=1 resolves each pixel's ray tree in one kernel (k_final_tree) instead of level by level."""
-    env = load("3d_room")
-    a = env.render((160, 90), time=0.3)
-    monkeypatch.setenv("EUCL_TREE_RESOLVE", "1")
-    b = env.render((160, 90), time=0.3)
-    assert np.array_equal(a.data, b.data) and b.stats["launches"] < a.stats["launches"]
+    for depth in (100, 64, 2**32 - 1):  # EUCL_MAX_LEVELS = 64 levels = max_depth <= 63; UINT32_MAX must not wrap
+        env.camera.max_depth = depth
+        with pytest.raises(eb.EuclError) as err:
+            env.render((8, 8))
+        assert err.value.status == -1
 
 
 @pytest.mark.parametrize("name", ["3d_room", "3d_hallways"])
