@@ -2,23 +2,28 @@
 """Headline benchmark: Mrays/s (ray segments per second) and frame time on a reference scene.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene 3d_room]
-                    [--width 3840 --height 2160] [--pipeline wavefront|megakernel]
+                    [--width 3840 --height 2160] [--pipeline wavefront|megakernel] [--no-configs]
 
 A "step" is one fixed-pose headless frame (Environment::render, src/universe/mod.rs:300-357).
  * value    : whole-job ray segments / second with the frame left in HBM (eucl_render_device)
  * e2e      : the same through the reference-facing call with a HOST output buffer
-              (Environment.render -> eucl_render; frame copied device->host every step)
- * roofline : FP64 issue roofline of the dominant kernel; the peak is
+              (Environment.render -> eucl_render; frame copied device->host every step).  At N > 1 every
+              rank writes its own row bands into ONE shared pinned host frame over its own PCIe link.
+ * roofline : FP64 issue roofline of k_intersect, the same definition at every N:
+              sum over ranks of segments x F_scene / slowest rank's k_intersect time, against N x the peak
               measured live by a DADD/DMUL/DFMA microbenchmark
  * cpu_baseline : the CPU oracle (restatement of the reference, oracle/) on a bounded sample
-`--impl reference` times the CPU oracle alone with all host threads (the Rust reference cannot be
-built here: no rustc/cargo).
+ * configs  : every BASELINE.json config measured in the same run (N = 1: all six; N > 1: the headline and
+              4d_room 7680x4320 at max_depth 10 and 16)
+`--impl reference` times the CPU oracle alone with all host threads, WHOLE frames (the Rust reference
+cannot be built here: no rustc/cargo).
 N > 1: one process per GPU (torchrun); interleaved row bands, one gather to rank 0, no other
-collective -- weak/strong: the frame is fixed, so scaling is "strong".
+collective -- the frame is fixed, so scaling is "strong".
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -41,6 +46,11 @@ DEFAULT_CONFIGS = {
     "3d_fresnel": (1920, 1080), "3d_room": (3840, 2160), "3d_hallways": (3840, 2160), "4d_frame": (3840, 2160),
     "4d_cylinders": (3840, 2160), "4d_room": (7680, 4320),
 }
+# BASELINE.json `configs`, in its order: (scene, width, height, max_depth or 0 = the reference's literal 10)
+ALL_CONFIGS = [("3d_fresnel", 1920, 1080, 0), ("3d_room", 3840, 2160, 0), ("3d_hallways", 3840, 2160, 0),
+               ("4d_frame", 3840, 2160, 0), ("4d_cylinders", 3840, 2160, 0), ("4d_room", 7680, 4320, 0),
+               ("4d_room", 7680, 4320, 16)]
+MULTI_GPU_CONFIGS = [("4d_room", 7680, 4320, 0), ("4d_room", 7680, 4320, 16)]
 
 
 def scene_flops_per_segment(env) -> int:
@@ -106,11 +116,12 @@ class ClockSampler:
 
 
 def oracle_sample(env, width, height, t, n_blocks=9, rows_per_block=8, threads=None):
-    """Times the CPU oracle on `n_blocks` row blocks spread over the frame; returns (segments, seconds, desc)."""
+    """Times the CPU oracle on `n_blocks` row blocks spread over the frame.
+    Returns (segments, seconds, rows actually rendered, description, threads)."""
     import oracle_api
 
     threads = threads or os.cpu_count() or 1
-    rows_per_block = min(rows_per_block, height)
+    rows_per_block = max(1, min(rows_per_block, height))
     n_blocks = max(1, min(n_blocks, height // rows_per_block))
     starts = [int((k + 0.5) * height / n_blocks - rows_per_block / 2) for k in range(n_blocks)]
     segs, secs = 0, 0.0
@@ -120,12 +131,15 @@ def oracle_sample(env, width, height, t, n_blocks=9, rows_per_block=8, threads=N
         _, _, st = oracle_api.render(env, width, height, time=t, threads=threads, rows=(r0, r0 + rows_per_block))
         secs += time.perf_counter() - t0
         segs += st["segments"]
-    return segs, secs, f"{n_blocks} blocks x {rows_per_block} rows of the {width}x{height} frame, spread evenly", threads
+    rows = n_blocks * rows_per_block
+    return segs, secs, rows, f"{n_blocks} blocks x {rows_per_block} rows of the {width}x{height} frame, spread evenly", threads
 
 
 def run_reference(args, width, height):
-    """--impl reference: the CPU restatement of the reference's path, all host threads."""
+    """--impl reference: the CPU restatement of the reference's path, all host threads, whole frames
+    (`--ref-rows R` > 0 bounds a step to 9 blocks of R rows and extrapolates; the default renders every row)."""
     import euclider_b200 as eb
+    import oracle_api
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,24 +148,43 @@ def run_reference(args, width, height):
     if args.max_depth:
         env.camera.max_depth = args.max_depth
     threads = os.cpu_count() or 1
-    blocks = 9
-    for _ in range(args.warmup):
-        oracle_sample(env, width, height, args.time, n_blocks=2, rows_per_block=2)
-    seg_total, sec_total, desc = 0, 0.0, ""
-    for _ in range(args.steps):
-        segs, secs, desc, threads = oracle_sample(env, width, height, args.time, n_blocks=blocks, rows_per_block=args.ref_rows)
+    whole = args.ref_rows <= 0
+    seg_total, sec_total, rows_total, desc = 0, 0.0, 0, ""
+
+    def one_step():
+        if whole:
+            t0 = time.perf_counter()
+            _, _, st = oracle_api.render(env, width, height, time=args.time, threads=threads)
+            return st["segments"], time.perf_counter() - t0, height, f"whole {width}x{height} frames"
+        segs, secs, rows, d, _ = oracle_sample(env, width, height, args.time, n_blocks=9, rows_per_block=args.ref_rows, threads=threads)
+        return segs, secs, rows, d
+
+    # the driver's K and W also size the GPU arm, where a frame takes milliseconds: keep the CPU run within a few
+    # minutes by shortening the warm-up first, then the timed frames (never below 3), and say so in the line
+    steps, warmup = args.steps, args.warmup
+    budget_s = 240.0
+    _, probe_s, probe_rows, _ = one_step()
+    frame_s = probe_s * (height / probe_rows)
+    if whole and frame_s * (steps + warmup) > budget_s:
+        warmup = 0
+        steps = max(min(steps, 3), min(steps, int(budget_s / frame_s)))
+    for _ in range(max(0, warmup - 1)):
+        one_step()
+    for _ in range(steps):
+        segs, secs, rows, desc = one_step()
         seg_total += segs
         sec_total += secs
+        rows_total += rows
     value = seg_total / sec_total / 1e6
-    # frame time extrapolated from the sampled rows
-    sample_pixels = blocks * args.ref_rows * width
-    ms_frame = sec_total / args.steps * 1e3 * (width * height) / sample_pixels
+    ms_frame = sec_total / steps * 1e3 * (height / (rows_total / steps))
+    note = "whole frames: ms_per_step is measured" if whole else "ms_per_step extrapolated from the sampled rows to the full frame"
+    if steps != args.steps:
+        note += f"; {steps} timed frames instead of {args.steps} to bound the CPU run to ~{int(budget_s)} s"
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_frame, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_frame, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.scene} {width}x{height} max_depth {env.camera.max_depth} time {args.time}",
-                   "note": "ms_per_step extrapolated from the sampled rows to the full frame"},
+        "config": {"workload": f"{args.scene} {width}x{height} max_depth {env.camera.max_depth} time {args.time}", "note": note},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -165,6 +198,219 @@ _RESULT_OUT = sys.stdout
 def emit(obj) -> None:
     """The result lines go to the process's ORIGINAL stdout (see main)."""
     print(json.dumps(obj), file=_RESULT_OUT, flush=True)
+
+
+class Rig:
+    """One config (scene, frame size, depth) on this rank: device-resident steps, host-frame steps, teardown."""
+
+    def __init__(self, args, scene, width, height, max_depth, world, rank, local_rank):
+        import torch
+        import torch.distributed as dist
+
+        import euclider_b200 as eb
+        from euclider_b200 import bands
+
+        self.torch, self.dist, self.eb = torch, dist, eb
+        self.args, self.scene, self.width, self.height = args, scene, width, height
+        self.world, self.rank, self.local_rank = world, rank, local_rank
+        self.device = torch.device("cuda", local_rank)
+        env = eb.load_reference_scene(scene)
+        if max_depth:
+            env.camera.max_depth = max_depth
+        env.pipeline = eb.EUCL_PIPELINE_MEGAKERNEL if args.pipeline == "megakernel" else eb.EUCL_PIPELINE_WAVEFRONT
+        self.stream = torch.cuda.current_stream()
+        env.set_stream(self.stream.cuda_stream, device=local_rank)
+        self.env = env
+        self.band_rows = args.band_rows if world > 1 else 0
+        opts = eb.EuclRenderOpts(width=width, height=height, band_rows=self.band_rows, band_rank=rank, band_world=world)
+        self.my_rows = int(eb.lib().eucl_band_rows_for_rank(opts)) if world > 1 else height
+        self.frame_bytes = height * width * 3
+        self.peer = world > 1 and args.gather == "peer"
+        self.frame_ptr, self.frame, self.ipc_ptr = 0, None, None
+        if world == 1:
+            self.frame = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device)
+            self.frame_ptr = self.frame.data_ptr()
+        elif self.peer:
+            # One frame buffer on GPU 0, mapped into every rank through CUDA IPC: each rank's pack kernel
+            # stores its rows straight into it over NVLink, so the gather IS the last kernel of the frame.
+            handle = torch.zeros(eb._capi.EUCL_IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+            ptr = C.c_void_p()
+            if rank == 0:
+                eb._capi.check(eb.lib().eucl_device_malloc(local_rank, self.frame_bytes, C.byref(ptr)))
+                buf = (C.c_uint8 * eb._capi.EUCL_IPC_HANDLE_BYTES)()
+                eb._capi.check(eb.lib().eucl_ipc_export(ptr, buf))
+                handle.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+            dist.broadcast(handle, src=0)
+            if rank != 0:
+                buf = (C.c_uint8 * eb._capi.EUCL_IPC_HANDLE_BYTES)(*handle.cpu().tolist())
+                eb._capi.check(eb.lib().eucl_ipc_open(buf, local_rank, C.byref(ptr)))
+            self.ipc_ptr = ptr
+            self.frame_ptr = ptr.value
+            if rank == 0:  # torch view of the raw allocation (for --check)
+                fp = self.frame_ptr
+
+                class _Raw:
+                    __cuda_array_interface__ = {"shape": (height, width, 3), "typestr": "|u1", "data": (fp, False), "version": 2}
+                self.frame = torch.as_tensor(_Raw(), device=self.device)
+            # frame-complete flag: a stream-ordered all-reduce after each rank's last kernel; nothing blocks on the host
+            self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        else:
+            # NCCL gather of compact row blocks, scattered to frame rows on rank 0
+            self.d_rows = torch.empty((max(self.my_rows, 1), width, 3), dtype=torch.uint8, device=self.device)
+            self.frame = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device) if rank == 0 else None
+            self.rows_of = [torch.tensor(bands.local_rows(height, self.band_rows, r, world), dtype=torch.long, device=self.device)
+                            for r in range(world)]
+            max_rows = max(len(x) for x in self.rows_of)
+            self.send = torch.zeros((max_rows, width, 3), dtype=torch.uint8, device=self.device)
+            self.recv = [torch.empty_like(self.send) for _ in range(world)] if rank == 0 else None
+        # host frame of the e2e leg: pinned; at N > 1 ONE frame in shared memory that every rank maps and pins
+        self.shm_path, self.host_np, self.sync_np, self.host_pinned = None, None, None, False
+        if world == 1:
+            self.host = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory()
+            self.host_np = self.host.numpy()
+            self.host_pinned = True
+        else:
+            name = [f"/dev/shm/eucl_bench_{os.getpid()}_{scene}_{width}x{height}"] if rank == 0 else [None]
+            if rank == 0:
+                with open(name[0], "wb") as f:
+                    f.truncate(self.frame_bytes + 4096)
+            dist.broadcast_object_list(name, src=0)
+            self.shm_path = name[0]
+            mm = np.memmap(self.shm_path, dtype=np.uint8, mode="r+", shape=(self.frame_bytes + 4096,))
+            self.mm = mm
+            self.host_np = mm[:self.frame_bytes].reshape(height, width, 3)
+            self.sync_np = mm[self.frame_bytes:self.frame_bytes + 8 * world].view(np.int64)  # one arrival counter per rank
+            self.host_pinned = eb.lib().eucl_host_register(C.c_void_p(mm.ctypes.data), mm.nbytes) == 0
+            self.e2e_frames = 0
+            dist.barrier()
+
+    # -- the value leg: frame stays in HBM ---------------------------------------------------------
+    def step(self, profile=False):
+        a, env = self.args, self.env
+        if self.world == 1 or self.peer:
+            st = env.render_device(self.frame_ptr, (self.width, self.height), a.time, device=self.local_rank,
+                                   band_rows=self.band_rows, band_rank=self.rank, band_world=self.world, compact_rows=False,
+                                   profile=profile)
+            if self.peer:  # the frame is complete when every rank's rows have landed: device-side, stream-ordered
+                self.dist.all_reduce(self.flag)
+            return st
+        st = env.render_device(self.d_rows.data_ptr(), (self.width, self.height), a.time, device=self.local_rank,
+                               band_rows=self.band_rows, band_rank=self.rank, band_world=self.world, compact_rows=True,
+                               profile=profile)
+        self.send[:self.my_rows].copy_(self.d_rows[:self.my_rows])
+        self.dist.gather(self.send, self.recv, dst=0)
+        if self.rank == 0:
+            for r in range(self.world):
+                self.frame.index_copy_(0, self.rows_of[r], self.recv[r][:len(self.rows_of[r])])
+        return st
+
+    # -- the e2e leg: the reference-facing call with a HOST frame ----------------------------------
+    def e2e_step(self):
+        a, env = self.args, self.env
+        img = env.render((self.width, self.height), a.time, device=self.local_rank, out=self.host_np,
+                         band_rows=self.band_rows, band_rank=self.rank, band_world=self.world)
+        if self.world > 1:  # frame complete = every rank has copied its bands into the shared host frame
+            self.e2e_frames += 1
+            self.sync_np[self.rank] = self.e2e_frames
+            while int(self.sync_np.min()) < self.e2e_frames:
+                pass
+        return img.stats
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def close(self):
+        eb = self.eb
+        self.sync_all()
+        if self.shm_path is not None:
+            if self.host_pinned:
+                eb.lib().eucl_host_unregister(C.c_void_p(self.mm.ctypes.data))
+            self.host_np = self.sync_np = None
+            del self.mm
+            self.dist.barrier()
+            if self.rank == 0:
+                try:
+                    os.unlink(self.shm_path)
+                except OSError:
+                    pass
+        self.env.set_stream(0, device=self.local_rank)
+        self.frame = None
+        if self.ipc_ptr is not None:
+            if self.rank != 0:
+                eb.lib().eucl_ipc_close(self.ipc_ptr)
+            self.dist.barrier()
+            if self.rank == 0:
+                eb.lib().eucl_device_free(self.local_rank, self.ipc_ptr)
+        self.env.close()
+        self.torch.cuda.empty_cache()
+
+
+def measure(rig: Rig, steps: int, warmup: int, sample_clocks: bool):
+    """Device-timed value leg, profile pass, e2e leg.  Returns a dict on rank 0, None elsewhere."""
+    torch, dist = rig.torch, rig.dist
+    world, rank = rig.world, rig.rank
+    for _ in range(max(warmup, 3)):
+        rig.step()
+    rig.sync_all()
+    sampler = ClockSampler(rig.local_rank) if (sample_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    segs, launches, retries, own_ms, grouping = 0, 0, 0, 0.0, 0
+    ev0.record(rig.stream)
+    for _ in range(steps):
+        st = rig.step()
+        segs += st["segments"]
+        launches += st["launches"]
+        retries += st["retries"]
+        own_ms += st["ms_total"]
+        grouping = st["ray_grouping"]
+    ev1.record(rig.stream)
+    rig.sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    prof = rig.step(profile=True)  # per-kernel-family device times (extra events; outside the timed region)
+    rig.sync_all()
+    t = torch.tensor([ms, float(segs), float(launches), float(retries), own_ms / steps, prof["ms_intersect"], float(prof["segments"])],
+                     dtype=torch.float64, device=rig.device)
+    if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        allt = torch.stack(allt).cpu().numpy()
+    else:
+        allt = t.cpu().numpy()[None, :]
+    ms = float(allt[:, 0].max())
+    segs, launches, retries = int(allt[:, 1].sum()), int(allt[:, 2].sum()), int(allt[:, 3].sum())
+    # end to end: host frame, copies inside the timed region, wall clock between barriers
+    for _ in range(2):
+        rig.e2e_step()
+    rig.sync_all()
+    t0 = time.perf_counter()
+    e2e_segs = 0
+    for _ in range(steps):
+        e2e_segs += rig.e2e_step()["segments"]
+    rig.sync_all()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([e2e_s, float(e2e_segs)], dtype=torch.float64, device=rig.device)
+    if world > 1:
+        tm, ts = tt.clone(), tt.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_segs = float(tm[0]), float(ts[1])
+    if rank != 0:
+        return None
+    return {
+        "ms_per_step": ms / steps, "value": segs / (ms * 1e-3) / 1e6, "segments_per_frame": segs / steps, "launches": launches,
+        "retries": retries, "clocks": clocks, "ray_grouping": int(grouping), "prof": prof,
+        "rank_ms": [round(float(v), 4) for v in allt[:, 4]],  # each rank's own device time per frame (CUDA events around its kernels)
+        "k_intersect_ms_max": float(allt[:, 5].max()), "prof_segments": float(allt[:, 6].sum()),
+        "e2e": {"value": e2e_segs / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s / steps * 1e3,
+                "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": rig.width * rig.height * 3,
+                "host_frame": ("pinned" if rig.host_pinned else "pageable") + (", shared by all ranks (each copies its own bands)" if world > 1 else "")},
+    }
 
 
 def main():
@@ -186,24 +432,27 @@ def main():
     ap.add_argument("--max-depth", type=int, default=0)
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--band-rows", type=int, default=16)
-    ap.add_argument("--ref-rows", type=int, default=32)
+    ap.add_argument("--ref-rows", type=int, default=None,
+                    help="CPU legs: rows per sampled block (reference arm default 0 = whole frames; cpu_baseline default 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the table of the other BASELINE.json configs")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: ranks store their rows into GPU 0's frame through CUDA IPC (peer) or NCCL gather")
-    ap.add_argument("--check", action="store_true", help="N > 1: compare the gathered frame with a single-GPU render")
+    ap.add_argument("--check", action="store_true", help="N > 1: compare the gathered frames with a single-GPU render")
     args = ap.parse_args()
     width, height = DEFAULT_CONFIGS.get(args.scene, (3840, 2160))
     width, height = args.width or width, args.height or height
 
     if args.impl == "reference":
+        args.ref_rows = 0 if args.ref_rows is None else args.ref_rows
         run_reference(args, width, height)
         return
+    args.ref_rows = 32 if args.ref_rows is None else args.ref_rows
 
     import torch
     import torch.distributed as dist
 
     import euclider_b200 as eb
-    from euclider_b200 import bands
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,210 +465,101 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    env = eb.load_reference_scene(args.scene)
-    if args.max_depth:
-        env.camera.max_depth = args.max_depth
-    env.pipeline = eb.EUCL_PIPELINE_MEGAKERNEL if args.pipeline == "megakernel" else eb.EUCL_PIPELINE_WAVEFRONT
-    stream = torch.cuda.current_stream()
-    env.set_stream(stream.cuda_stream, device=local_rank)
+    rig = Rig(args, args.scene, width, height, args.max_depth, world, rank, local_rank)
+    m = measure(rig, args.steps, args.warmup, sample_clocks=True)
+    env = rig.env
 
-    band_rows = args.band_rows if world > 1 else 0
-    opts = eb.EuclRenderOpts(width=width, height=height, band_rows=band_rows, band_rank=rank, band_world=world)
-    my_rows = int(eb.lib().eucl_band_rows_for_rank(opts)) if world > 1 else height
-    frame_bytes = height * width * 3
-    peer = world > 1 and args.gather == "peer"
-    frame_ptr, frame = 0, None
-    if world == 1:
-        frame = torch.empty((height, width, 3), dtype=torch.uint8, device=device)
-        frame_ptr = frame.data_ptr()
-    elif peer:
-        # One frame buffer on GPU 0, mapped into every rank through CUDA IPC: each rank's pack kernel
-        # stores its rows straight into it over NVLink, so the gather IS the last kernel of the frame.
-        import ctypes as C
-
-        handle = torch.zeros(eb._capi.EUCL_IPC_HANDLE_BYTES, dtype=torch.uint8, device=device)
-        ptr = C.c_void_p()
-        if rank == 0:
-            eb._capi.check(eb.lib().eucl_device_malloc(local_rank, frame_bytes, C.byref(ptr)))
-            buf = (C.c_uint8 * eb._capi.EUCL_IPC_HANDLE_BYTES)()
-            eb._capi.check(eb.lib().eucl_ipc_export(ptr, buf))
-            handle.copy_(torch.tensor(list(buf), dtype=torch.uint8))
-        dist.broadcast(handle, src=0)
-        if rank != 0:
-            buf = (C.c_uint8 * eb._capi.EUCL_IPC_HANDLE_BYTES)(*handle.cpu().tolist())
-            eb._capi.check(eb.lib().eucl_ipc_open(buf, local_rank, C.byref(ptr)))
-        frame_ptr = ptr.value
-        if rank == 0:  # torch view of the raw allocation (for the copy to the host)
-            class _Raw:
-                __cuda_array_interface__ = {"shape": (height, width, 3), "typestr": "|u1", "data": (frame_ptr, False),
-                                            "version": 2}
-            frame = torch.as_tensor(_Raw(), device=device)
-    else:
-        # NCCL gather of compact row blocks, scattered to frame rows on rank 0
-        d_rows = torch.empty((max(my_rows, 1), width, 3), dtype=torch.uint8, device=device)
-        frame = torch.empty((height, width, 3), dtype=torch.uint8, device=device) if rank == 0 else None
-        rows_of = []
-        for r in range(world):
-            idx = bands.local_rows(height, band_rows, r, world)
-            rows_of.append(torch.tensor(idx, dtype=torch.long, device=device))
-        max_rows = max(len(x) for x in rows_of)
-        send = torch.zeros((max_rows, width, 3), dtype=torch.uint8, device=device)
-        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-    host = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
-
-    def step(profile=False):
-        if world == 1 or peer:
-            st = env.render_device(frame_ptr, (width, height), args.time, device=local_rank, band_rows=band_rows,
-                                   band_rank=rank, band_world=world, compact_rows=False, profile=profile)
-            if peer:
-                dist.barrier()  # every rank's rows have landed in GPU 0's frame (render_device is synchronous)
-            return st
-        st = env.render_device(d_rows.data_ptr(), (width, height), args.time, device=local_rank, band_rows=band_rows,
-                               band_rank=rank, band_world=world, compact_rows=True, profile=profile)
-        send[:my_rows].copy_(d_rows[:my_rows])
-        dist.gather(send, recv, dst=0)
-        if rank == 0:
-            for r in range(world):
-                frame.index_copy_(0, rows_of[r], recv[r][:len(rows_of[r])])
-        return st
-
-    def frame_to_host():
-        """rank 0: device frame -> pinned host buffer (the e2e leg)."""
-        host.copy_(frame, non_blocking=False)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
-    sampler = ClockSampler(local_rank)
+    line = None
     if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    segs, launches, retries = 0, 0, 0
-    ev0.record(stream)
-    for _ in range(args.steps):
-        st = step()
-        segs += st["segments"]
-        launches += st["launches"]
-        retries += st["retries"]
-    ev1.record(stream)
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, float(segs), float(launches)], dtype=torch.float64, device=device)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, segs, launches = float(tmax[0]), int(tsum[1]), int(tsum[2])
-    ms_per_step = ms / args.steps
-    value = segs / (ms * 1e-3) / 1e6
-
-    if rank == 0 and world == 1:
-        # profile pass: per-kernel-family device times (extra events; not part of the timed region)
-        prof = step(profile=True)
-        # end-to-end through the reference-facing call with a pinned HOST frame buffer
-        host_np = host.numpy()
-        for _ in range(3):
-            env.render((width, height), args.time, device=local_rank, out=host_np)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_segs = 0
-        for _ in range(args.steps):
-            img = env.render((width, height), args.time, device=local_rank, out=host_np)
-            e2e_segs += img.stats["segments"]
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        e2e = {"value": e2e_segs / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_s / args.steps * 1e3,
-               "h2d_bytes_per_step": 256, "d2h_bytes_per_step": width * height * 3}
-    elif rank == 0:
-        prof = None
-        e2e = None  # N > 1: measured below (bands -> GPU 0 -> pinned host)
-    if world > 1:
-        # e2e at N GPUs: bands -> gather -> host copy on rank 0, timed by wall clock between barriers
-        sync_all()
-        t0 = time.perf_counter()
-        e2e_segs = 0
-        for _ in range(args.steps):
-            st = step()
-            e2e_segs += st["segments"]
-            if rank == 0:
-                frame_to_host()
-        sync_all()
-        e2e_s = time.perf_counter() - t0
-        tt = torch.tensor([e2e_s, float(e2e_segs)], dtype=torch.float64, device=device)
-        tm = tt.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = tt.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            e2e = {"value": float(ts[1]) / float(tm[0]) / 1e6, "unit": "Mrays/s", "ms_per_step": float(tm[0]) / args.steps * 1e3,
-                   "h2d_bytes_per_step": 256 * world, "d2h_bytes_per_step": width * height * 3}
-
-    if rank == 0:
-        import ctypes as C
-
         f_scene = scene_flops_per_segment(env)
         dadd, dmul, dfma = C.c_double(), C.c_double(), C.c_double()
         eb.lib().eucl_fp64_peak(local_rank, C.byref(dadd), C.byref(dmul), C.byref(dfma))
         peak = max(dadd.value, dmul.value)  # non-fused FP64 instruction rate, T op/s (-fmad=false build)
-        seg_per_frame = segs / args.steps / world if world > 1 else segs / args.steps
-        roofline = {"bound": "fp64_issue", "unit": "Tflop/s", "peak": peak, "peak_source": "measured live (DADD/DMUL microbenchmark)",
-                    "peak_dfma_tops": dfma.value, "traffic": None, "flops_per_segment": f_scene}
-        if args.scene == "3d_room" and (width, height) == (3840, 2160):
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_intersect launch (level 8 of a whole-frame chunk,
-            # 4.15 M rays) from the committed ncu --set full capture (profiles/r1d_ncu_k_intersect_level8.txt).
-            # Algorithmic bytes of that launch: none beyond its queue records (ray 52 B in, hit 64 B out per ray =
-            # 482 MB); the frame itself is 3 B/pixel, written by k_final.
-            roofline["traffic"] = 353.219328e6 + 294.449664e6
-            roofline["traffic_note"] = "one level-8 k_intersect launch, 4.15 M rays, ncu --set full capture (profiles/r1d_*)"
-        if prof is not None and prof["ms_intersect"] > 0:
-            achieved = prof["segments"] * f_scene / (prof["ms_intersect"] * 1e-3) / 1e12
-            roofline.update({"kernel": "k_intersect (all levels of one frame)", "achieved": achieved, "frac": achieved / peak,
-                             "kernel_ms_per_frame": prof["ms_intersect"],
-                             "family_ms": {k: prof[k] for k in ("ms_raygen", "ms_intersect", "ms_shade", "ms_resolve", "ms_total")}})
-        else:
-            achieved = value * 1e6 * f_scene / 1e12
-            roofline.update({"kernel": "whole frame", "achieved": achieved, "frac": achieved / (peak * world)})
+        achieved = m["prof_segments"] * f_scene / (m["k_intersect_ms_max"] * 1e-3) / 1e12 if m["k_intersect_ms_max"] > 0 else None
+        roofline = {
+            "bound": "fp64_issue", "unit": "Tflop/s", "peak": peak * world,
+            "peak_source": f"measured live (DADD/DMUL microbenchmark on rank 0) x {world} GPU(s)", "peak_dfma_tops": dfma.value,
+            "traffic": None, "traffic_note": "not measured in this run; dram__bytes of the kernels are in the ncu captures under profiles/",
+            "flops_per_segment": f_scene, "kernel": "k_intersect, light + heavy build, all levels of one frame (slowest rank)",
+            "achieved": achieved, "frac": achieved / (peak * world) if achieved else None, "kernel_ms_per_frame": m["k_intersect_ms_max"],
+            "family_ms": {k: m["prof"][k] for k in ("ms_raygen", "ms_intersect", "ms_shade", "ms_resolve", "ms_total")},
+        }
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
             try:
-                c_segs, c_secs, desc, threads = oracle_sample(env, width, height, args.time, rows_per_block=args.ref_rows)
+                c_segs, c_secs, _, desc, threads = oracle_sample(env, width, height, args.time, rows_per_block=args.ref_rows)
                 cpu = {"value": c_segs / c_secs / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": desc}
             except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU number
                 cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "metric": "Mrays/s", "value": m["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.scene} {width}x{height} max_depth {env.camera.max_depth} time {args.time}",
-                       "pipeline": args.pipeline, "segments_per_frame": seg_per_frame * (world if world > 1 else 1),
-                       "parallelism": (f"row bands of {band_rows} x {world} ranks, "
-                                       + ("peer stores into GPU 0's frame (CUDA IPC over NVLink)" if peer else "NCCL gather to rank 0"))
+                       "pipeline": args.pipeline, "segments_per_frame": m["segments_per_frame"],
+                       "ray_grouping": m["ray_grouping"],  # what the per-scene tuner settled on (EuclStats.ray_grouping)
+                       "parallelism": (f"row bands of {rig.band_rows} x {world} ranks, "
+                                       + ("peer stores into GPU 0's frame (CUDA IPC over NVLink), frame-complete flag = "
+                                          "stream-ordered all-reduce" if rig.peer else "NCCL gather to rank 0"))
                        if world > 1 else "single GPU",
                        "l2": "node arena (GBs per chunk) is far larger than the 126 MB L2; no explicit flush"},
-            "fps": 1e3 / ms_per_step, "e2e": e2e, "gpu_launches": launches, "retries": retries, "clocks": clocks,
+            "fps": 1e3 / m["ms_per_step"], "e2e": m["e2e"], "gpu_launches": m["launches"], "retries": m["retries"],
+            "clocks": m["clocks"], "rank_device_ms": {"min": min(m["rank_ms"]), "max": max(m["rank_ms"]), "per_rank": m["rank_ms"]},
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        emit(line)
+    check_results = []
     if world > 1 and args.check:
-        step()
-        sync_all()
+        check_results.append(check_gather(rig, args))
+    rig.close()
+
+    # the other configs of BASELINE.json, same run, fewer frames each
+    if not args.no_configs and args.pipeline == "wavefront":
+        table = []
+        todo = ALL_CONFIGS if world == 1 else MULTI_GPU_CONFIGS
+        k = max(3, min(args.steps, 6))
+        for scene, w, h, depth in todo:
+            r2 = Rig(args, scene, w, h, depth, world, rank, local_rank)
+            m2 = measure(r2, k, 3, sample_clocks=False)
+            if rank == 0:
+                f2 = scene_flops_per_segment(r2.env)
+                ach = m2["prof_segments"] * f2 / (m2["k_intersect_ms_max"] * 1e-3) / 1e12 if m2["k_intersect_ms_max"] > 0 else None
+                table.append({"scene": scene, "width": w, "height": h, "max_depth": int(r2.env.camera.max_depth), "steps": k,
+                              "ms_per_step": m2["ms_per_step"], "fps": 1e3 / m2["ms_per_step"], "mrays_per_s": m2["value"],
+                              "segments_per_frame": m2["segments_per_frame"], "e2e_mrays_per_s": m2["e2e"]["value"],
+                              "e2e_ms_per_step": m2["e2e"]["ms_per_step"], "flops_per_segment": f2,
+                              "k_intersect_frac": ach / (peak * world) if ach else None, "ray_grouping": m2["ray_grouping"],
+                              "retries": m2["retries"], "rank_device_ms": [min(m2["rank_ms"]), max(m2["rank_ms"])]})
+            if world > 1 and args.check:
+                check_results.append(check_gather(r2, args))
+            r2.close()
         if rank == 0:
-            frame_to_host()
-            env.set_stream(0, device=local_rank)
-            whole = env.render((width, height), args.time, device=local_rank)
-            same = bool(np.array_equal(whole.data, host.numpy()))
-            emit({"check": "gathered frame == single-GPU frame", "equal": same})
+            line["configs"] = table
+    if rank == 0:
+        emit(line)
+        for c in check_results:
+            emit(c)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def check_gather(rig: Rig, args):
+    """N > 1: the gathered device frame and the shared host frame against a single-GPU render on rank 0."""
+    rig.step()
+    rig.e2e_step()
+    rig.sync_all()
+    res = None
+    if rig.rank == 0:
+        gathered = rig.frame.cpu().numpy()
+        shared = np.array(rig.host_np)
+        rig.env.set_stream(0, device=rig.local_rank)
+        whole = rig.env.render((rig.width, rig.height), args.time, device=rig.local_rank)
+        rig.env.set_stream(rig.stream.cuda_stream, device=rig.local_rank)
+        res = {"check": f"{rig.scene} {rig.width}x{rig.height}: gathered frames == single-GPU frame",
+               "device_frame_equal": bool(np.array_equal(whole.data, gathered)),
+               "host_frame_equal": bool(np.array_equal(whole.data, shared))}
+    rig.sync_all()
+    return res
 
 
 if __name__ == "__main__":

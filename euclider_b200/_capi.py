@@ -96,7 +96,7 @@ class EuclRenderOpts(C.Structure):
 class EuclStats(C.Structure):
     _fields_ = [("pixels", C.c_uint64), ("segments", C.c_uint64), ("nodes", C.c_uint64),
                 ("level_counts", C.c_uint64 * EUCL_MAX_LEVELS), ("levels", C.c_uint32), ("retries", C.c_uint32),
-                ("launches", C.c_uint32), ("_pad", C.c_uint32), ("ms_total", C.c_float), ("ms_raygen", C.c_float),
+                ("launches", C.c_uint32), ("ray_grouping", C.c_uint32), ("ms_total", C.c_float), ("ms_raygen", C.c_float),
                 ("ms_intersect", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float)]
 
 
@@ -146,6 +146,8 @@ PROTOTYPES = {
     "eucl_camera_rotate_plane4": (C.c_int, [C.POINTER(EuclCamera), C.c_int, C.c_int, C.c_double]),
     "eucl_device_malloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "eucl_device_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "eucl_host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "eucl_host_unregister": (C.c_int, [C.c_void_p]),
     "eucl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eucl_ipc_open": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "eucl_ipc_close": (C.c_int, [C.c_void_p]),

@@ -61,7 +61,9 @@ struct EuclScene {
     int dim = 3;
     int sm_count = 148;
     int blob_bytes = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0;  // staged scene + plane_chain scratch
+    size_t smem_scene = 0;  // staged scene only
+    unsigned long long shade_light_mask = 1ull, shade_heavy_mask = 0ull;
     uint8_t* d_blob = nullptr;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> tex_objects;
@@ -78,6 +80,7 @@ struct EuclScene {
     DeviceBuffer path_io;  // eucl_trace_path staging
     DeviceBuffer rorder;   // per-reach-key node lists of the next level
     int n_cull = 0;
+    int light_capable = 0;
     // Grouping rays by reach key pays on scenes whose deep levels bounce around a few bounded objects
     // (3d_room: -13 % frame time) and costs a little elsewhere, so it is auto-tuned per scene: the
     // first two retry-free frames run with and without it, the faster setting is kept.  The picture
@@ -90,6 +93,8 @@ struct EuclScene {
     int n_entities = 0;
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
+    int list_capacity = 0;     // entries per index list (bins, reach keys): the largest LEVEL a chunk may have
+    double list_factor = 1.0;  // ... in nodes per pixel (level 0 has exactly one; deeper levels are smaller in every shipped scene)
     int32_t* h_small = nullptr; // pinned mirror of the counters
 };
 
@@ -674,6 +679,26 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
             h.cull_root[h.n_cull++] = de.node_root;
     }
     s->n_cull = h.n_cull;
+    // per-entity classification for the closest-hit loops; a scene is "light-capable" when a ray with reach key 0
+    // can only meet primitives and root plane chains (k_intersect<LIGHT>)
+    std::vector<int32_t> ent_flags((size_t)std::max(flat->n_entities, 1), 0);
+    bool light_capable = true;
+    for (int e = 0; e < flat->n_entities; ++e) {
+        const EuclEntity& de = dev_entities[(size_t)e];
+        if (de.surface < 0) continue;
+        const MNode& root = mb.out[(size_t)de.node_root];
+        int fl = ENT_SURFACED;
+        if (root.kind == M_PRIM) fl |= ENT_PRIM;
+        else if (root.kind == M_CHAIN && de.node_first == de.node_root && (root.b & 0x4000) && (root.b & 0x3fff) <= kPlaneChainMax) fl |= ENT_ROOT_PLANES;
+        for (int k = 0; k < h.n_cull; ++k)
+            if (h.cull_root[k] == de.node_root) fl |= ENT_CULL_ROOT;
+        if (!(fl & (ENT_PRIM | ENT_ROOT_PLANES | ENT_CULL_ROOT))) light_capable = false;
+        ent_flags[(size_t)e] = fl;
+    }
+    if (!env_int("EUCL_INTERSECT_SPLIT", 1)) light_capable = false; // diagnostics: one build intersects every ray
+    h.light_capable = light_capable ? 1 : 0;
+    s->light_capable = h.light_capable;
+    h.off_ent_flags = w.put(ent_flags.data(), ent_flags.size());
     h.off_entities = w.put(dev_entities.data(), dev_entities.size());
     h.off_materials = w.put(flat->materials, (size_t)flat->n_materials);
     h.off_transforms = w.put(flat->transforms, (size_t)flat->n_transforms);
@@ -692,7 +717,24 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     std::memcpy(w.bytes.data(), &h, sizeof h);
     s->blob_bytes = h.blob_bytes;
     // staged scene + the per-thread plane_chain scratch columns (kernels.cu: plane_scratch)
-    s->smem_bytes = scene_smem_bytes(h.blob_bytes) + sizeof(double) * kPlaneChainMax * kBlock;
+    s->smem_scene = scene_smem_bytes(h.blob_bytes);
+    s->smem_bytes = s->smem_scene + sizeof(double) * kPlaneChainMax * kBlock;
+    // shade bins of the light build of k_shade: the miss bin and the bins of every entity whose surface has a uniform
+    // reflection ratio and the identity threshold direction; the heavy build (Fresnel, Snell) shades the others
+    s->shade_light_mask = 1ull;
+    s->shade_heavy_mask = 0ull;
+    if (kBinsPerEntity * flat->n_entities + 1 <= kMaxBins)
+        for (int e = 0; e < flat->n_entities; ++e) {
+            const int sf = flat->entities[e].surface;
+            if (sf < 0) continue;
+            const bool simple = flat->surfaces[sf].ratio_op == EUCL_RATIO_UNIFORM && flat->surfaces[sf].thr_op == EUCL_THR_IDENTITY;
+            const unsigned long long bits = ((1ull << kBinsPerEntity) - 1ull) << (1 + kBinsPerEntity * e);
+            (simple ? s->shade_light_mask : s->shade_heavy_mask) |= bits;
+        }
+    if (env_int("EUCL_SHADE_SPLIT", 1) == 0) { // one build shades every bin (diagnostics)
+        s->shade_heavy_mask |= s->shade_light_mask;
+        s->shade_light_mask = 0ull;
+    }
     int smem_optin = 0;
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (s->smem_bytes > (size_t)smem_optin)
@@ -700,7 +742,7 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
                                               " B) exceed the shared memory of one CTA (" + std::to_string(smem_optin) + " B)");
     EUCL_CUDA_S(cudaMalloc((void**)&s->d_blob, w.bytes.size()));
     EUCL_CUDA_S(cudaMemcpy(s->d_blob, w.bytes.data(), w.bytes.size(), cudaMemcpyHostToDevice));
-    EUCL_CUDA_S(configure_kernels(s->smem_bytes));
+    EUCL_CUDA_S(configure_kernels(s->smem_bytes, s->smem_scene));
     EUCL_CUDA_S(cudaMallocHost((void**)&s->h_small, sizeof(int32_t) * kSmallInts));
 #undef EUCL_CUDA_S
     *out = s;
@@ -750,25 +792,24 @@ void frame_params(const EuclCamera& cam, const EuclRenderOpts& o, FrameParams* f
 }
 
 size_t arena_bytes(int dim, size_t cap) {
-    size_t per = (size_t)dim * 16 * 2 + 4 + sizeof(HitInfo) + sizeof(NodeMeta) + 32;
+    size_t per = (size_t)dim * 16 + 4 + sizeof(HitRec) + sizeof(NodeMeta) + 32;
     return per * cap + 16 * 16;
 }
 
-Workspace carve(EuclScene* s, int dim, int cap) {
+Workspace carve(EuclScene* s, int dim, int cap, int list_cap) {
     Workspace ws{};
     ws.capacity = cap;
+    ws.list_cap = list_cap;
     uint8_t* p = (uint8_t*)s->nodes.ptr;
     auto take = [&](size_t bytes) {
         uint8_t* r = p;
         p += align16(bytes);
         return r;
     };
-    ws.ray_od = (double2*)take((size_t)dim * 16 * cap);
-    ws.hit_pn = (double2*)take((size_t)dim * 16 * cap);
-    ws.res_rg = (double2*)take((size_t)16 * cap);
-    ws.res_ba = (double2*)take((size_t)16 * cap);
+    ws.ray = (double*)take((size_t)dim * 16 * cap);
+    ws.hit = (HitRec*)take(sizeof(HitRec) * (size_t)cap);
+    ws.res = (double*)take((size_t)32 * cap);
     ws.meta = (NodeMeta*)take(sizeof(NodeMeta) * (size_t)cap);
-    ws.hit_ei = (HitInfo*)take(sizeof(HitInfo) * (size_t)cap);
     ws.ray_cur = (int32_t*)take((size_t)4 * cap);
     int32_t* small = (int32_t*)s->small.ptr;
     ws.count = small + SmallLayout::count;
@@ -816,16 +857,17 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         if (s->arena_factor <= 0.0) s->arena_factor = std::max(1.0, (double)env_int("EUCL_ARENA_FACTOR_X10", 45) / 10.0);
         // queue kernels run as ONE wave of resident CTAs (512 threads per SM at 128 registers) walking their level with a grid
         // stride: measured faster than 2-8 waves on glass scenes (3d_room 20.7 -> 20.0 ms), equal elsewhere
-        Launch l{s->stream, s->d_blob, s->smem_bytes,
+        Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene,
                  s->sm_count * std::max(1, env_int("EUCL_BLOCKS_PER_SM", kResidentThreads / kBlock)),
-                 s->sm_count * std::max(1, env_int("EUCL_MEM_BLOCKS_PER_SM", 8))};
+                 s->sm_count * std::max(1, env_int("EUCL_LIGHT_BLOCKS_PER_SM", kLightResidentBlocks)),
+                 s->sm_count * std::max(1, env_int("EUCL_MEM_BLOCKS_PER_SM", 8)),
+                 s->shade_light_mask, s->shade_heavy_mask,
+                 s->sm_count * std::max(1, env_int("EUCL_LIGHT_K2_BLOCKS_PER_SM", kLightK2ResidentBlocks)), s->light_capable, s->n_cull};
         const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
         const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && kBinsPerEntity * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
-        auto workspace_bytes = [&](size_t cap) {
-            return arena_bytes(dim, cap) + (want_rorder ? sizeof(int32_t) * (size_t)kRayBins * cap : 0) +
-                   (want_order ? sizeof(int32_t) * (size_t)(kBinsPerEntity * s->n_entities + 1) * cap : 0);
-        };
+        const size_t n_lists = (want_rorder ? (size_t)kRayBins : 0) + (want_order ? (size_t)(kBinsPerEntity * s->n_entities + 1) : 0);
+        auto workspace_bytes = [&](size_t cap, size_t list_cap) { return arena_bytes(dim, cap) + sizeof(int32_t) * n_lists * list_cap; };
 
         for (int row0 = 0; row0 < (int)my_rows;) {
             ChunkParams cp{};
@@ -839,28 +881,34 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                 cp.n_pixels = cp.n_rows * width;
                 long long want = (long long)std::ceil((double)rows_per_chunk * (double)width * s->arena_factor) + 1024;
                 if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) want = 16;
-                bool too_big = want > 0x7fff0000ll;
-                if (!too_big && (int)want > s->arena_capacity) {
+                long long want_list = (long long)std::ceil((double)rows_per_chunk * (double)width * s->list_factor) + 1024;
+                if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) want_list = 16;
+                bool too_big = want > 0x7fff0000ll || want_list > 0x7fff0000ll;
+                if (!too_big && ((int)want > s->arena_capacity || (int)want_list > s->list_capacity)) {
                     EUCL_CUDA(cudaStreamSynchronize(s->stream));
+                    want = std::max<long long>(want, s->arena_capacity);
+                    want_list = std::max<long long>(want_list, s->list_capacity);
                     size_t free_b = 0, total_b = 0;
                     EUCL_CUDA(cudaMemGetInfo(&free_b, &total_b));
                     const size_t held = s->nodes.bytes + s->order.bytes + s->rorder.bytes;
                     size_t budget = (size_t)((double)(free_b + held) * 0.85);
                     const int cap_mb = env_int("EUCL_ARENA_MAX_MB", 0);
                     if (cap_mb > 0) budget = std::min(budget, (size_t)cap_mb << 20);
-                    too_big = workspace_bytes((size_t)want) > budget;
+                    too_big = workspace_bytes((size_t)want, (size_t)want_list) > budget;
                     if (!too_big) {
                         cudaError_t e = s->nodes.ensure(arena_bytes(dim, (size_t)want));
-                        if (e == cudaSuccess && want_rorder) e = s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want);
-                        if (e == cudaSuccess && want_order) e = s->order.ensure(sizeof(int32_t) * (size_t)(kBinsPerEntity * s->n_entities + 1) * (size_t)want);
+                        if (e == cudaSuccess && want_rorder) e = s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want_list);
+                        if (e == cudaSuccess && want_order) e = s->order.ensure(sizeof(int32_t) * (size_t)(kBinsPerEntity * s->n_entities + 1) * (size_t)want_list);
                         if (e == cudaSuccess) {
                             s->arena_capacity = (int)want;
+                            s->list_capacity = (int)want_list;
                         } else { // leave a consistent (empty) workspace behind and try a smaller chunk
                             cudaGetLastError();
                             s->nodes.release();
                             s->rorder.release();
                             s->order.release();
                             s->arena_capacity = 0;
+                            s->list_capacity = 0;
                             if (e != cudaErrorMemoryAllocation) return fail(EUCL_ERR_CUDA, std::string("workspace allocation: ") + cudaGetErrorString(e));
                             too_big = true;
                         }
@@ -872,7 +920,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     rows_per_chunk = (rows_per_chunk + 1) / 2;
                     continue;
                 }
-                Workspace ws = carve(s, dim, s->arena_capacity);
+                Workspace ws = carve(s, dim, s->arena_capacity, s->list_capacity);
                 EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));
                 // profile mode: one event after every launch; family = 0 raygen, 1 intersect, 2 shade, 3 resolve
                 std::vector<int> prof_family;
@@ -916,14 +964,14 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     dbg("k_raygen", 0);
                     mark(0);
                     for (int level = 0; level < (int)cam->max_depth; ++level) {
-                        launch_intersect(dim, l, ws, level);
+                        st.launches += launch_intersect(dim, l, ws, level);
                         dbg("k_intersect", level);
                         mark(1);
-                        launch_shade(dim, l, fp, cp, ws, level, d_hit);
+                        st.launches += launch_shade(dim, l, fp, cp, ws, level, d_hit);
                         dbg("k_shade", level);
                         mark(2);
                     }
-                    launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
+                    st.launches += launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
                     dbg("k_shade", (int)cam->max_depth);
                     mark(2);
                     for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
@@ -934,7 +982,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     dbg("k_final", 0);
                     mark(3);
                     if (!fault.empty()) return fail(EUCL_ERR_CUDA, "EUCL_DEBUG_SYNC: " + fault);
-                    st.launches += 3 + 2 * cam->max_depth + (cam->max_depth == 0 ? 0 : cam->max_depth - 1);
+                    st.launches += 2 + (cam->max_depth == 0 ? 0 : cam->max_depth - 1); // raygen, final, resolve levels
                 }
                 EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
                                           s->stream));
@@ -967,8 +1015,12 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     // levels after the overflowing one were skipped, so the counts are a lower bound only
                     long long need = 0;
                     for (uint32_t lv = 0; lv <= cam->max_depth; ++lv) need += s->h_small[SmallLayout::count + lv];
-                    double factor = (double)need / (double)cp.n_pixels * 1.05 + 0.05;
-                    s->arena_factor = std::max(s->arena_factor * 1.5, factor);
+                    if (s->h_small[SmallLayout::overflow] == 3) { // a level outgrew the index lists (they hold one level each)
+                        s->list_factor = std::max(s->list_factor * 1.5, 1.0);
+                    } else {
+                        double factor = (double)need / (double)cp.n_pixels * 1.05 + 0.05;
+                        s->arena_factor = std::max(s->arena_factor * 1.5, factor);
+                    }
                     st.retries += 1;
                     if (st.retries > 32) return fail(EUCL_ERR_OUT_OF_MEMORY, "node arena keeps overflowing");
                     continue;
@@ -1005,6 +1057,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         }
     }
     s->warm_frames++;
+    st.ray_grouping = s->ray_bins_now && s->rorder.ptr != nullptr && o->pipeline == EUCL_PIPELINE_WAVEFRONT ? 1u : 0u;
     if (stats) *stats = st;
     return EUCL_OK;
 }
@@ -1040,22 +1093,41 @@ int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     if (st != EUCL_OK) return st;
     if (!out_rgb8) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render: null output");
     EUCL_CUDA(cudaSetDevice(s->device));
-    const size_t rows = o->compact_rows ? eucl_band_rows_for_rank(o) : o->height;
+    // A rank of a band-split render (band_world > 1) renders its rows compactly on the device and then copies
+    // each band to its place in the caller's frame: rows of other ranks are never read or written, so N ranks can
+    // fill ONE host frame (shared pinned memory) over their own PCIe links at the same time.
+    const bool scatter = !o->compact_rows && o->band_world > 1;
+    const size_t my_rows = eucl_band_rows_for_rank(o);
+    const size_t rows = (o->compact_rows || scatter) ? my_rows : o->height;
     const size_t pixels = rows * (size_t)o->width;
     const bool want_hit = o->want_hit_ids && out_hit_ids;
-    EUCL_CUDA(s->frame.ensure(pixels * 3));
-    if (want_hit) EUCL_CUDA(s->hit_ids.ensure(pixels * 4));
-    const bool partial = !o->compact_rows && o->band_world > 1;
-    if (partial) { // rows of other ranks are left untouched in the caller's buffer: stage them in
-        EUCL_CUDA(cudaMemcpyAsync(s->frame.ptr, out_rgb8, pixels * 3, cudaMemcpyHostToDevice, s->stream));
-        if (want_hit) EUCL_CUDA(cudaMemcpyAsync(s->hit_ids.ptr, out_hit_ids, pixels * 4, cudaMemcpyHostToDevice, s->stream));
-    }
+    EUCL_CUDA(s->frame.ensure(std::max<size_t>(pixels, 1) * 3));
+    if (want_hit) EUCL_CUDA(s->hit_ids.ensure(std::max<size_t>(pixels, 1) * 4));
     EuclRenderOpts opts = *o;
     opts.want_hit_ids = want_hit ? 1 : 0;
+    if (scatter) opts.compact_rows = 1;
     st = render_impl(s, cam, &opts, (uint8_t*)s->frame.ptr, want_hit ? (int32_t*)s->hit_ids.ptr : nullptr, stats);
     if (st != EUCL_OK) return st;
-    EUCL_CUDA(cudaMemcpyAsync(out_rgb8, s->frame.ptr, pixels * 3, cudaMemcpyDeviceToHost, s->stream));
-    if (want_hit) EUCL_CUDA(cudaMemcpyAsync(out_hit_ids, s->hit_ids.ptr, pixels * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (!scatter) {
+        EUCL_CUDA(cudaMemcpyAsync(out_rgb8, s->frame.ptr, pixels * 3, cudaMemcpyDeviceToHost, s->stream));
+        if (want_hit) EUCL_CUDA(cudaMemcpyAsync(out_hit_ids, s->hit_ids.ptr, pixels * 4, cudaMemcpyDeviceToHost, s->stream));
+    } else if (my_rows > 0) {
+        // band k of this rank: compact rows [k * band, ...) -> frame rows [(k * world + rank) * band, ...)
+        const size_t band = o->band_rows ? o->band_rows : o->height, world = o->band_world;
+        const size_t full = my_rows / band, tail = my_rows % band; // whole bands, rows of a last partial band
+        auto copy_bands = [&](void* dst, const void* src, size_t px_bytes) -> cudaError_t {
+            const size_t band_bytes = band * o->width * px_bytes;
+            uint8_t* d = (uint8_t*)dst + (size_t)o->band_rank * band_bytes;
+            cudaError_t e = cudaSuccess;
+            if (full) e = cudaMemcpy2DAsync(d, world * band_bytes, src, band_bytes, band_bytes, full, cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess && tail)
+                e = cudaMemcpyAsync(d + full * world * band_bytes, (const uint8_t*)src + full * band_bytes, tail * o->width * px_bytes,
+                                    cudaMemcpyDeviceToHost, s->stream);
+            return e;
+        };
+        EUCL_CUDA(copy_bands(out_rgb8, s->frame.ptr, 3));
+        if (want_hit) EUCL_CUDA(copy_bands(out_hit_ids, s->hit_ids.ptr, 4));
+    }
     EUCL_CUDA(cudaStreamSynchronize(s->stream));
     return EUCL_OK;
 }
@@ -1084,7 +1156,7 @@ int eucl_trace_path(EuclScene* s, const double* location, const double* directio
         h_in[D + k] = direction[k];
     }
     EUCL_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, s->stream));
-    Launch l{s->stream, s->d_blob, s->smem_bytes, 1, 1};
+    Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene, 1, 1, 1, 1ull, 0ull, 1, 0, 0};
     launch_trace_path(D, l, d_in, distance, d_out, d_found);
     double h_out[2 * EUCL_MAX_DIM];
     int h_found = 0;
@@ -1113,6 +1185,19 @@ int eucl_device_free(int device, void* d_ptr) {
     if (!d_ptr) return EUCL_OK;
     EUCL_CUDA(cudaSetDevice(device));
     EUCL_CUDA(cudaFree(d_ptr));
+    return EUCL_OK;
+}
+
+int eucl_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_host_register: bad argument");
+    if (eucl_device_count() <= 0) return fail(EUCL_ERR_NO_DEVICE, "no CUDA device available");
+    EUCL_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return EUCL_OK;
+}
+
+int eucl_host_unregister(void* ptr) {
+    if (!ptr) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_host_unregister: null argument");
+    EUCL_CUDA(cudaHostUnregister(ptr));
     return EUCL_OK;
 }
 

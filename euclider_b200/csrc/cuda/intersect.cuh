@@ -321,12 +321,58 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         ts[i * ts_stride] = t;
         if (!(t < 0.0)) exists |= 1u << i; // NaN and +inf pass
     }
+    const bool want_in = op == EUCL_CSG_INTERSECTION;
+    if (first_only) {
+        // Shortcut for an entity's whole shape (only the first item of the stream is asked for, mod.rs:110-112).  Let m be
+        // the existing hit whose distance is STRICTLY smaller than every other existing one (no NaN anywhere).  If m
+        // passes the membership test against every other leaf (outside all of them for a Union, inside all for an
+        // Intersection), m is the first item of the final list: it enters the fold as `b` at its own step, where it is
+        // closer than every item of the list so far and is tested against the fold of the earlier leaves; at every later
+        // step it is the head of `a`, closer than the new `b`, and is tested against that one leaf.  Each of these tests
+        // is one of the N - 1 evaluated here, so m is emitted first every time.  (Rays inside a room or a box: always.)
+        // Anything else -- ties, NaN, a rejected m -- takes the general evaluation below.
+        int m = -1;
+        double tm = 0.0;
+        bool clean = true;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            if (!((exists >> i) & 1u)) continue;
+            const double t = ts[i * ts_stride];
+            if (isnan(t)) clean = false;
+            if (m < 0 || t < tm) {
+                m = i;
+                tm = t;
+            }
+        }
+        if (m < 0) {
+            list_out = 0ull;
+            return 0;
+        }
+        if (clean) {
+            const Vec<D> pm = d * tm + o;
+            bool ok = true;
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) {
+                const double* r = rec + j * kPlaneStride;
+                Vec<D> nrm;
+#pragma unroll
+                for (int k = 0; k < D; ++k) nrm[k] = r[k];
+                const double v = dot(nrm, pm) + r[4];
+                const bool in = !isnan(v) && ((__double2hiint(v) < 0) == (r[5] < 0.0));
+                const bool tie = j != m && ((exists >> j) & 1u) && !(tm < ts[j * ts_stride]);
+                if (j != m && (in != want_in || tie)) ok = false;
+            }
+            if (ok) {
+                list_out = (unsigned long long)m;
+                return 1;
+            }
+        }
+    }
     // inside bit (i, j): half-space j contains the hit point of leaf i (shape.rs:873-881):
     // signum == (n.p + c).signum(); Rust signum is +-1 by sign bit and NaN for NaN.
     // Hit points are processed in groups of G kept in registers while a rolled loop walks the
     // planes, so each plane record is loaded once per group and the loop body stays small.
     unsigned long long inside = 0ull;
-    const bool want_in = op == EUCL_CSG_INTERSECTION;
     const unsigned all = (1u << N) - 1u;
     if (N % 3 == 0) {
         for (int i0 = 0; i0 < N; i0 += 3) plane_rows<D, 3>(rec, N, o, d, ts, ts_stride, i0, inside);
@@ -555,6 +601,35 @@ __device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec
             found = csg_first<D>(sv, ent.node_first, ent.node_root, o, d, ts, ts_stride, h);
         }
         if (found && (best.entity < 0 || best.t > h.t)) best = ClosestHit{e, h.prim, h.flags, h.t};
+    }
+    return best;
+}
+
+// trace_closest for rays whose reach key is 0 in a "light-capable" scene (SceneHeader::light_capable): every
+// surfaced entity is one primitive, one root chain of half-spaces, or a cull root -- and a ray with key 0 stays
+// outside the bound of every cull root, so those yield no hit (same argument as ray_misses) and are skipped
+// without a test.  No general CSG evaluator, no hit arena: the kernel built on this keeps more warps resident.
+template <int D>
+__device__ __forceinline__ ClosestHit closest_hit_light(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, double* ts,
+                                                        int ts_stride) {
+    ClosestHit best{-1, 0, 0, 0.0};
+    for (int e = 0; e < sv.n_entities; ++e) {
+        const int flags = sv.ent_flags()[e];
+        if (!(flags & ENT_SURFACED) || (flags & ENT_CULL_ROOT)) continue;
+        const MNode root = reinterpret_cast<const MNode*>(sv.nodes())[sv.entities()[e].node_root];
+        double t0 = 0.0, t1 = 0.0;
+        int prim = root.a;
+        bool found;
+        if (flags & ENT_PRIM) {
+            found = prim_roots<D>(sv, root.a, o, d, t0, t1) > 0;
+        } else { // ENT_ROOT_PLANES
+            unsigned long long L = 0ull;
+            found = plane_chain<D>(sv, root.b >> 16, root.a, root.b & 0x3fff, o, d, true, ts, ts_stride, L) > 0;
+            const int idx = (int)(L & 15ull);
+            t0 = ts[idx * ts_stride];
+            prim = root.a + idx;
+        }
+        if (found && (best.entity < 0 || best.t > t0)) best = ClosestHit{e, prim, 0, t0};
     }
     return best;
 }

@@ -25,10 +25,11 @@ namespace {
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// node arena access (planes of double2 -> 128-bit coalesced transactions)
+// node arena access (array-of-structures records made of 128-bit words)
 
 template <int D>
 __device__ __forceinline__ void store_ray(const Workspace& ws, int node, const Vec<D>& o, const Vec<D>& d, int cur) {
+    double2* rec = reinterpret_cast<double2*>(ws.ray + (size_t)node * (2 * D));
     double v[2 * D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -36,15 +37,16 @@ __device__ __forceinline__ void store_ray(const Workspace& ws, int node, const V
         v[D + k] = d[k];
     }
 #pragma unroll
-    for (int k = 0; k < D; ++k) ws.ray_od[(size_t)k * ws.capacity + node] = make_double2(v[2 * k], v[2 * k + 1]);
+    for (int k = 0; k < D; ++k) rec[k] = make_double2(v[2 * k], v[2 * k + 1]);
     ws.ray_cur[node] = cur;
 }
 template <int D>
 __device__ __forceinline__ void load_ray(const Workspace& ws, int node, Vec<D>& o, Vec<D>& d) {
+    const double2* rec = reinterpret_cast<const double2*>(ws.ray + (size_t)node * (2 * D));
     double v[2 * D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        double2 t = ws.ray_od[(size_t)k * ws.capacity + node];
+        double2 t = rec[k];
         v[2 * k] = t.x;
         v[2 * k + 1] = t.y;
     }
@@ -54,38 +56,26 @@ __device__ __forceinline__ void load_ray(const Workspace& ws, int node, Vec<D>& 
         d[k] = v[D + k];
     }
 }
-template <int D>
-__device__ __forceinline__ void store_hit(const Workspace& ws, int node, const Vec<D>& p, const Vec<D>& n) {
-    double v[2 * D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        v[k] = p[k];
-        v[D + k] = n[k];
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) ws.hit_pn[(size_t)k * ws.capacity + node] = make_double2(v[2 * k], v[2 * k + 1]);
+__device__ __forceinline__ void store_hit(const Workspace& ws, int node, const HitRec& h) {
+    double2* rec = reinterpret_cast<double2*>(ws.hit + node);
+    rec[0] = make_double2(h.t, h.cos_raw);
+    int4 w = make_int4(h.entity, h.prim, h.flags, h.exiting);
+    reinterpret_cast<int4*>(rec)[1] = w;
 }
-template <int D>
-__device__ __forceinline__ void load_hit(const Workspace& ws, int node, Vec<D>& p, Vec<D>& n) {
-    double v[2 * D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        double2 t = ws.hit_pn[(size_t)k * ws.capacity + node];
-        v[2 * k] = t.x;
-        v[2 * k + 1] = t.y;
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        p[k] = v[k];
-        n[k] = v[D + k];
-    }
+__device__ __forceinline__ HitRec load_hit(const Workspace& ws, int node) {
+    const double2* rec = reinterpret_cast<const double2*>(ws.hit + node);
+    const double2 a = rec[0];
+    const int4 w = reinterpret_cast<const int4*>(rec)[1];
+    return HitRec{a.x, a.y, w.x, w.y, w.z, w.w};
 }
 __device__ __forceinline__ void store_res(const Workspace& ws, int node, const Rgba& c) {
-    ws.res_rg[node] = make_double2(c.r, c.g);
-    ws.res_ba[node] = make_double2(c.b, c.a);
+    double2* rec = reinterpret_cast<double2*>(ws.res + (size_t)node * 4);
+    rec[0] = make_double2(c.r, c.g);
+    rec[1] = make_double2(c.b, c.a);
 }
 __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
-    double2 rg = ws.res_rg[node], ba = ws.res_ba[node];
+    const double2* rec = reinterpret_cast<const double2*>(ws.res + (size_t)node * 4);
+    const double2 rg = rec[0], ba = rec[1];
     return Rgba{rg.x, rg.y, ba.x, ba.y};
 }
 
@@ -129,18 +119,20 @@ struct ShadeOut {
 
 // ComposableSurface::get_color up to (not including) the recursive trace calls
 // (surface.rs:62-162): decides which children exist and where they start.
-template <int D>
+// GLASS = false compiles the Fresnel / Snell providers out: the light shade kernel only ever sees surfaces
+// with a uniform reflection ratio and the identity threshold direction (the host routes the bins).
+template <int D, bool GLASS>
 __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
                                           bool exiting, double cos_raw, const Vec<D>& p, const Vec<D>& n_raw,
                                           ShadeOut<D>& out) {
     const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
     const Vec<D> n_closer = exiting ? -n_raw : n_raw;
     const double cos_closer = exiting ? -cos_raw : cos_raw;
-    const bool needs_theta = sf.ratio_op == EUCL_RATIO_FRESNEL || sf.thr_op == EUCL_THR_SNELL;
+    const bool needs_theta = GLASS && (sf.ratio_op == EUCL_RATIO_FRESNEL || sf.thr_op == EUCL_THR_SNELL);
     const double from_theta = needs_theta ? angle_from_cos(-cos_closer) : 0.0;
     RefractionCache rc{needs_theta ? dm_sin(from_theta) : 0.0, 0.0, 0.0, false};
     // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
-    const double ratio = fmax(fmin(reflection_ratio<D>(sf, from_theta, exiting, rc), 1.0), 0.0);
+    const double ratio = fmax(fmin(reflection_ratio<D, GLASS>(sf, from_theta, exiting, rc), 1.0), 0.0);
     out.ratio = ratio;
     out.q = 0u;
     out.flags = 0u;
@@ -156,7 +148,7 @@ __device__ __forceinline__ void shade_hit(const SceneView& sv, double time_milli
             out.flags |= NODE_HAS_SC;
             have_t = true;
         } else {
-            Vec<D> td = threshold_direction<D>(sf, dir, n_closer, exiting, from_theta, rc);
+            Vec<D> td = threshold_direction<D, GLASS>(sf, dir, n_closer, exiting, from_theta, rc);
             const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
             const int dest = exiting ? material_at<D>(sv, new_origin) : ent;
             if (dest >= 0) {
@@ -243,78 +235,111 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
     Vec<D> loc;
 #pragma unroll
     for (int k = 0; k < D; ++k) loc[k] = fp.location[k];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
-        const int local_row = cp.local_row0 + i / fp.width;
-        const int x = i % fp.width;
+    const unsigned lane = threadIdx.x & 31u;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cp.n_pixels; base += gridDim.x * blockDim.x) {
+        const int i = base + (int)lane;
+        const bool valid = i < cp.n_pixels;
+        const int local_row = cp.local_row0 + (valid ? i : 0) / fp.width;
+        const int x = (valid ? i : 0) % fp.width;
         const int y = frame_row_of_local(cp, local_row);
-        if (belongs_to < 0) {
-            store_res(ws, i, checkerboard(x, y));
-            ws.meta[i] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF | NODE_FINAL_RGB};
-            ws.ray_cur[i] = -1;
-            if (hit_ids_out) hit_ids_out[(size_t)(cp.compact_rows ? local_row : y) * fp.width + x] = -2;
+        if (belongs_to < 0) { // the same for every pixel of the frame
+            if (valid) {
+                store_res(ws, i, checkerboard(x, y));
+                ws.meta[i] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF | NODE_FINAL_RGB};
+                ws.ray_cur[i] = -1;
+                if (hit_ids_out) hit_ids_out[(size_t)(cp.compact_rows ? local_row : y) * fp.width + x] = -2;
+            }
             continue;
         }
         Vec<D> dir = camera_ray<D>(fp, x, y);
         material_enter<D>(sv, belongs_to, dir);
-        store_ray<D>(ws, i, loc, dir, belongs_to);
+        if (valid) store_ray<D>(ws, i, loc, dir, belongs_to);
+        if (ws.ray_bins) { // group the primary rays by reach key like k_shade groups the children (one atomicAdd per warp and key)
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const int key = reach_key<D>(sv, loc, dir);
+                const unsigned peers = __match_any_sync(active, key);
+                const int leader = __ffs(peers) - 1;
+                int s2 = 0;
+                if ((int)lane == leader) s2 = atomicAdd(&ws.rbin_count[key], __popc(peers));
+                s2 = __shfl_sync(peers, s2, leader);
+                ws.rorder[(size_t)key * ws.list_cap + s2 + __popc(peers & ((1u << lane) - 1u))] = i;
+            }
+        }
     }
 }
 
 // K2: closest hit of every ray of one level.
-template <int D>
-__global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level) {
+//
+// Two builds share a level when its rays are grouped by reach key and the scene allows it (SceneHeader::light_capable):
+// the LIGHT one walks the rays with key 0 -- they can only hit primitives and root plane chains -- without the CSG
+// evaluator and its per-thread hit arena, at a fraction of the registers; the HEAVY one walks the other keys (or every
+// ray when the level is not grouped).  `key_mask` selects the reach-key lists of a launch.
+template <int D, bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? kLightBlock : kBlock, LIGHT ? EUCL_INTERSECT_LIGHT_MIN_BLOCKS : EUCL_INTERSECT_MIN_BLOCKS)
+    k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level, unsigned key_mask) {
     // an earlier level did not fit: the host grows the arena and retries.  One decision per block (see k_shade).
-    __shared__ int s_skip;
-    if (threadIdx.x == 0) s_skip = *ws.overflow != 0;
-    __syncthreads();
-    if (s_skip) return;
+    __shared__ int s_skip, s_total;
+    __shared__ int s_rprefix[kRayBins + 1];
     const int off = ws.level_off[level], cnt = ws.count[level];
-    if (blockIdx.x == 0 && threadIdx.x == 0) ws.level_off[level + 1] = off + cnt;
-    if (blockIdx.x * blockDim.x >= cnt) return;
+    const bool grouped = ws.ray_bins != 0;
+    if (threadIdx.x == 0) {
+        // no ray at all when the camera is in no entity (checkerboard frame, mod.rs:385-396)
+        s_skip = *ws.overflow != 0 || *ws.cam_entity < 0;
+        int acc = cnt;
+        if (grouped) {
+            acc = 0;
+            for (int b = 0; b < kRayBins; ++b) {
+                s_rprefix[b] = acc;
+                if ((key_mask >> b) & 1u) acc += ws.rbin_count[level * kRayBins + b];
+            }
+            s_rprefix[kRayBins] = acc;
+        }
+        s_total = acc;
+        if (blockIdx.x == 0) ws.level_off[level + 1] = off + cnt;
+    }
+    __syncthreads();
+    const int total = s_total;
+    if (s_skip || blockIdx.x * blockDim.x >= total) return;
     const SceneView& sv = stage_scene(blob);
     double* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
-    // levels >= 1: the shade kernel of the previous level grouped this level's rays by reach key
-    __shared__ int s_rprefix[kRayBins + 1];
-    const bool grouped = ws.ray_bins != 0 && level > 0;
-    if (grouped && threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < kRayBins; ++b) {
-            s_rprefix[b] = acc;
-            acc += ws.rbin_count[level * kRayBins + b];
+    int bin = 0; // the lists of a launch are walked front to back: the cursor only moves forward
+    auto node_at = [&](int i) -> int {
+        if (i >= total) return -1;
+        if (!grouped) return off + i;
+        while (i >= s_rprefix[bin + 1]) ++bin;
+        return ws.rorder[(size_t)bin * ws.list_cap + (i - s_rprefix[bin])];
+    };
+    int node_next = node_at(blockIdx.x * blockDim.x + threadIdx.x);
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
+        int node = node_next;
+        node_next = node_at(base + stride + (int)lane);
+        bool valid = node >= 0;
+        if (grouped && valid && (node < off || node >= off + cnt)) { // must not happen: reported, never dereferenced
+            *ws.overflow = 2;
+            valid = false;
         }
-        s_rprefix[kRayBins] = acc;
-    }
-    __syncthreads();
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cnt; base += stride) {
-        const int i = base + (int)lane;
-        int node = off + i;
-        bool valid = i < cnt;
-        if (grouped && valid) {
-            int b = 0;
-            while (b < kRayBins - 1 && i >= s_rprefix[b + 1]) ++b;
-            node = ws.rorder[(size_t)b * ws.capacity + (i - s_rprefix[b])];
-            if (i >= s_rprefix[kRayBins] || node < off || node >= off + cnt) { // must not happen: reported, never dereferenced
-                *ws.overflow = 2;
-                valid = false;
-                node = off;
-            }
-        }
-        valid = valid && ws.ray_cur[node] >= 0;
         int ent = -1;
         bool exiting_flag = false;
         double cos_hint = 0.0;
         if (valid) {
-            Vec<D> o, d, p, n;
+            Vec<D> o, d;
             load_ray<D>(ws, node, o, d);
-            bool exiting = false;
-            double cos_raw = 0.0;
-            ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, ts, (int)blockDim.x);
-            ws.hit_ei[node] = HitInfo{ent, exiting ? 1 : 0, cos_raw};
-            exiting_flag = exiting;
-            cos_hint = cos_raw;
-            if (ent >= 0) store_hit<D>(ws, node, p, n);
+            const ClosestHit h = LIGHT ? closest_hit_light<D>(sv, o, d, ts, (int)blockDim.x) : closest_hit<D>(sv, o, d, ts, (int)blockDim.x);
+            HitRec rec{0.0, 0.0, -1, 0, 0, 0};
+            if (h.entity >= 0) { // orientation of the winner relative to the ray (mod.rs:114-125)
+                Vec<D> p, n;
+                hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n);
+                const double cos_raw = angle_cos(d, n);
+                const bool exiting = angle_from_cos(cos_raw) < kFracPi2;
+                rec = HitRec{h.t, cos_raw, h.entity, h.prim, h.flags, exiting ? 1 : 0};
+                exiting_flag = exiting;
+                cos_hint = cos_raw;
+            }
+            ent = h.entity;
+            store_hit(ws, node, rec);
         }
         if (ws.n_bins > 1) {
             // group the level's nodes by hit entity so that a shading warp runs ONE surface program:
@@ -338,7 +363,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
                 int slot = 0;
                 if ((int)lane == leader) slot = atomicAdd(&ws.bin_count[level * kMaxBins + key], __popc(peers));
                 slot = __shfl_sync(peers, slot, leader);
-                ws.order[(size_t)key * ws.capacity + slot + __popc(peers & ((1u << lane) - 1u))] = node;
+                ws.order[(size_t)key * ws.list_cap + slot + __popc(peers & ((1u << lane) - 1u))] = node;
             }
         }
     }
@@ -346,52 +371,68 @@ __global__ void __launch_bounds__(kBlock, EUCL_INTERSECT_MIN_BLOCKS) k_intersect
 
 // K3: shade every node of one level and append its children to the next level.  Children are
 // appended with one atomicAdd per warp (ballot + popc ranks).
-template <int D, bool RAY_BINS>
-__global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
-                                                  Workspace ws, int level, int32_t* __restrict__ hit_ids_out) {
+//
+// Two builds of the kernel share a level: the LIGHT one (GLASS = false) shades the bins whose surfaces have a
+// uniform reflection ratio and the identity threshold direction -- walls, mirrors, tinted and opaque objects --
+// plus the rays that hit nothing; without the Fresnel / Snell / general_rotation code it needs far fewer registers
+// and keeps more warps resident.  The HEAVY one (GLASS = true) shades the remaining bins (and everything when the
+// level is not binned).  `bin_mask` selects the bins of a launch.
+template <int D, bool RAY_BINS, bool GLASS>
+__global__ void __launch_bounds__(GLASS ? kBlock : kLightBlock, GLASS ? EUCL_SHADE_MIN_BLOCKS : EUCL_SHADE_LIGHT_MIN_BLOCKS)
+    k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp, Workspace ws, int level, unsigned long long bin_mask,
+            int32_t* __restrict__ hit_ids_out) {
     const int off = ws.level_off[level], cnt = ws.count[level];
-    if (blockIdx.x * blockDim.x >= cnt) return;
+    const bool last_level = level >= fp.max_depth; // depth 0: background without intersecting (mod.rs:157,183)
+    // binned levels: position g of the concatenated bins of this launch -> (bin, index) through the bin prefix sums
+    __shared__ int s_prefix[kMaxBins + 1];
     // An overflow flagged by an EARLIER kernel means this level's queue is incomplete: skip it (the host
     // retries with a larger arena).  Blocks of THIS launch set the flag too, so the decision must be taken
     // once per block: threads reading the flag on their own could disagree, and the ones that left would
     // be missing from the cooperative scene staging below (a partially staged scene = wild table offsets).
-    __shared__ int s_skip;
-    if (threadIdx.x == 0) s_skip = level > 0 && *ws.overflow != 0;
+    __shared__ int s_skip, s_total;
+    const bool binned = ws.n_bins > 1 && !last_level;
+    if (threadIdx.x == 0) {
+        s_skip = level > 0 && *ws.overflow != 0;
+        int acc = cnt;
+        if (binned) {
+            acc = 0;
+            for (int b = 0; b < ws.n_bins; ++b) {
+                s_prefix[b] = acc;
+                if ((bin_mask >> b) & 1ull) acc += ws.bin_count[level * kMaxBins + b];
+            }
+            s_prefix[ws.n_bins] = acc;
+        }
+        s_total = acc;
+    }
     __syncthreads();
-    if (s_skip) return;
+    const int total = s_total;
+    if (s_skip || blockIdx.x * blockDim.x >= total) return;
     const SceneView& sv = stage_scene(blob);
-    const bool last_level = level >= fp.max_depth; // depth 0: background without intersecting (mod.rs:157,183)
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
-    // binned levels: position g of the concatenated bins -> (bin, index) through the bin prefix sums
-    __shared__ int s_prefix[kMaxBins + 1];
-    const bool binned = ws.n_bins > 1 && !last_level;
-    if (binned && threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < ws.n_bins; ++b) {
-            s_prefix[b] = acc;
-            acc += ws.bin_count[level * kMaxBins + b];
-        }
-        s_prefix[ws.n_bins] = acc;
-    }
-    __syncthreads();
-    const int total = binned ? s_prefix[ws.n_bins] : cnt;
+    // node of position g; the bins of a launch are walked front to back, so the bin cursor only moves forward
+    int bin = 0;
+    auto node_at = [&](int g) -> int {
+        if (g >= total) return -1;
+        if (!binned) return off + g;
+        while (g >= s_prefix[bin + 1]) ++bin;
+        return ws.order[(size_t)bin * ws.list_cap + (g - s_prefix[bin])];
+    };
+    int node_next = node_at(blockIdx.x * blockDim.x + threadIdx.x);
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
-        const int g = base + (int)lane;
-        int node = off + g;
-        bool valid = g < total;
-        if (binned && valid) {
-            int b = 0;
-            while (g >= s_prefix[b + 1]) ++b;
-            node = ws.order[(size_t)b * ws.capacity + (g - s_prefix[b])];
-            if (node < off || node >= off + cnt) { // must not happen: reported, never dereferenced
-                *ws.overflow = 2;
-                valid = false;
-                node = off;
-            }
-        } else if (valid) {
-            valid = ws.ray_cur[node] >= 0;
+        int node = node_next;
+        node_next = node_at(base + stride + (int)lane); // the index of the next iteration travels while this one computes
+        bool valid = node >= 0;
+        if (binned && valid && (node < off || node >= off + cnt)) { // must not happen: reported, never dereferenced
+            *ws.overflow = 2;
+            valid = false;
+        }
+        if (!valid) node = off;
+        int cur = -1;
+        if (valid) {
+            cur = ws.ray_cur[node];
+            valid = cur >= 0; // checkerboard pixels carry no ray
         }
         const int i = node - off;
         ShadeOut<D> so;
@@ -401,8 +442,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
         if (valid) {
             Vec<D> o, d;
             load_ray<D>(ws, node, o, d);
-            const int cur = ws.ray_cur[node];
-            const HitInfo ei = last_level ? HitInfo{-1, 0, 0.0} : ws.hit_ei[node];
+            const HitRec ei = last_level ? HitRec{0.0, 0.0, -1, 0, 0, 0} : load_hit(ws, node);
             if (level == 0 && hit_ids_out) {
                 const int local_row = cp.local_row0 + i / fp.width;
                 const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
@@ -412,23 +452,24 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
                 store_res(ws, node, mapped_color<D>(sv, sv.background, d)); // background.get_color(direction.to_point())
                 ws.meta[node] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF};
             } else {
-                Vec<D> p, n;
-                load_hit<D>(ws, node, p, n);
-                shade_hit<D>(sv, fp.time_millis, d, cur, ei.entity, ei.exiting != 0, ei.cos_raw, p, n, so);
+                Vec<D> p, n; // location and normal as the intersector reports them, from the compact hit
+                hit_geometry<D>(sv, ei.prim, ei.flags, o, d, ei.t, p, n);
+                shade_hit<D, GLASS>(sv, fp.time_millis, d, cur, ei.entity, ei.exiting != 0, ei.cos_raw, p, n, so);
                 shaded = true;
             }
         }
         int so_tchild = -1, so_rchild = -1;
         // warp-aggregated append of the children to level + 1: one atomicAdd per warp
         const unsigned tmask = __ballot_sync(0xffffffffu, so.t_emit), rmask = __ballot_sync(0xffffffffu, so.r_emit);
-        const int nt = __popc(tmask), total = nt + __popc(rmask);
+        const int nt = __popc(tmask), n_children = nt + __popc(rmask);
         int slot = 0;
-        if (total > 0) {
-            if (lane == 0) slot = atomicAdd(&ws.count[level + 1], total);
+        if (n_children > 0) {
+            if (lane == 0) slot = atomicAdd(&ws.count[level + 1], n_children);
             slot = __shfl_sync(0xffffffffu, slot, 0);
         }
-        const bool fits = total > 0 && (long long)next_off + slot + total <= (long long)ws.capacity;
-        if (total > 0 && !fits && lane == 0) *ws.overflow = 1;
+        const bool fits_arena = (long long)next_off + slot + n_children <= (long long)ws.capacity;
+        const bool fits = n_children > 0 && fits_arena && slot + n_children <= ws.list_cap; // the index lists hold one level each
+        if (n_children > 0 && !fits && lane == 0) *ws.overflow = fits_arena ? 3 : 1;
         if (shaded) {
             const unsigned lt = (1u << lane) - 1u;
             int tchild = -1, rchild = -1;
@@ -466,7 +507,7 @@ __global__ void __launch_bounds__(kBlock, EUCL_SHADE_MIN_BLOCKS) k_shade(const u
                     int s2 = 0;
                     if ((int)lane == leader) s2 = atomicAdd(&ws.rbin_count[(level + 1) * kRayBins + key], __popc(peers));
                     s2 = __shfl_sync(peers, s2, leader);
-                    ws.rorder[(size_t)key * ws.capacity + s2 + __popc(peers & ((1u << lane) - 1u))] = child;
+                    ws.rorder[(size_t)key * ws.list_cap + s2 + __popc(peers & ((1u << lane) - 1u))] = child;
                 }
             };
             bin_child(so_tchild, so.t.o, so.t.d);
@@ -585,7 +626,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
                 val = mapped_color<D>(sv, sv.background, d);
             } else {
                 ShadeOut<D> so;
-                shade_hit<D>(sv, fp.time_millis, d, cur, ent, exiting, cos_raw, p, n, so);
+                shade_hit<D, true>(sv, fp.time_millis, d, cur, ent, exiting, cos_raw, p, n, so);
                 if (so.flags & NODE_UNDEFINED) {
                     val = Rgba{0.0, 0.0, 0.0, 0.0};
                     atomicAdd(ws.undefined_count, 1ull);
@@ -754,30 +795,70 @@ inline int grid_for(int n, int block, int grid_max) {
     } while (0)
 
 void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws) {
-    EUCL_DISPATCH_DIM(dim, (k_camera_entity<3><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, fp, ws)),
-                      (k_camera_entity<4><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, fp, ws)));
+    EUCL_DISPATCH_DIM(dim, (k_camera_entity<3><<<1, 32, l.smem_scene, l.stream>>>(l.blob, fp, ws)),
+                      (k_camera_entity<4><<<1, 32, l.smem_scene, l.stream>>>(l.blob, fp, ws)));
 }
 void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                    int32_t* hit_ids_out) {
     const int grid = grid_for(cp.n_pixels, kBlock, l.grid_mem);
-    EUCL_DISPATCH_DIM(dim, (k_raygen<3><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)),
-                      (k_raygen<4><<<grid, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)));
+    EUCL_DISPATCH_DIM(dim, (k_raygen<3><<<grid, kBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)),
+                      (k_raygen<4><<<grid, kBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)));
 }
-void launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
-    EUCL_DISPATCH_DIM(dim, (k_intersect<3><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level)),
-                      (k_intersect<4><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level)));
-}
-void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
-                  int32_t* hit_ids_out) {
-    if (ws.ray_bins && level + 1 < fp.max_depth) { // the next level will be intersected: group its rays
-        EUCL_DISPATCH_DIM(dim,
-                          (k_shade<3, true><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
-                          (k_shade<4, true><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
-    } else {
-        EUCL_DISPATCH_DIM(dim,
-                          (k_shade<3, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
-                          (k_shade<4, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
+int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
+    // grouped level of a light-capable scene: key 0 -> light build, the other keys -> heavy build;
+    // a light-capable scene without cull roots (every ray has key 0) runs the light build in node order
+    const bool light_all = l.light_capable && l.n_cull == 0;
+    const bool split = l.light_capable && ws.ray_bins != 0;
+    const size_t smem_light = l.smem_scene + sizeof(double) * kPlaneChainMax * kLightBlock;
+    int launches = 0;
+    if (light_all || split) {
+        EUCL_DISPATCH_DIM(dim, (k_intersect<3, true><<<l.grid_light_k2, kLightBlock, smem_light, l.stream>>>(l.blob, ws, level, 1u)),
+                          (k_intersect<4, true><<<l.grid_light_k2, kLightBlock, smem_light, l.stream>>>(l.blob, ws, level, 1u)));
+        ++launches;
     }
+    if (!light_all) {
+        const unsigned mask = split ? 0xfffeu : 0xffffu;
+        EUCL_DISPATCH_DIM(dim, (k_intersect<3, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level, mask)),
+                          (k_intersect<4, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level, mask)));
+        ++launches;
+    }
+    return launches;
+}
+template <int D, bool RAY_BINS, bool GLASS>
+static void launch_shade_one(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
+                             unsigned long long mask, int32_t* hit_ids_out) {
+    if (GLASS) k_shade<D, RAY_BINS, true><<<l.grid_max, kBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
+    else k_shade<D, RAY_BINS, false><<<l.grid_light, kLightBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
+}
+template <int D, bool GLASS>
+static void launch_shade_dim(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
+                             unsigned long long mask, int32_t* hit_ids_out) {
+    if (ws.ray_bins && level + 1 < fp.max_depth) launch_shade_one<D, true, GLASS>(l, fp, cp, ws, level, mask, hit_ids_out); // the next level will be intersected: group its rays
+    else launch_shade_one<D, false, GLASS>(l, fp, cp, ws, level, mask, hit_ids_out);
+}
+int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
+                 int32_t* hit_ids_out) {
+    const bool last_level = level >= fp.max_depth;
+    unsigned long long light = l.shade_light_mask, heavy = l.shade_heavy_mask;
+    if (last_level) { // background lookups only
+        light = ~0ull;
+        heavy = 0ull;
+    } else if (ws.n_bins <= 1) { // not binned: one kernel that can shade everything
+        light = 0ull;
+        heavy = ~0ull;
+    }
+    int launches = 0;
+    if (light) {
+        EUCL_DISPATCH_DIM(dim, (launch_shade_dim<3, false>(l, fp, cp, ws, level, light, hit_ids_out)),
+                          (launch_shade_dim<4, false>(l, fp, cp, ws, level, light, hit_ids_out)));
+        ++launches;
+    }
+    if (heavy) {
+        EUCL_DISPATCH_DIM(dim, (launch_shade_dim<3, true>(l, fp, cp, ws, level, heavy, hit_ids_out)),
+                          (launch_shade_dim<4, true>(l, fp, cp, ws, level, heavy, hit_ids_out)));
+        ++launches;
+    }
+    return launches;
 }
 void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level) {
     (void)dim;
@@ -801,45 +882,52 @@ void launch_trace_path(int dim, const Launch& l, const double* d_in, double dist
                       (k_trace_path<4><<<1, 32, l.smem_bytes, l.stream>>>(l.blob, d_in, distance, d_out, d_found)));
 }
 
-cudaError_t configure_kernels(size_t smem_bytes) {
-    // Shared-memory carveout of the two hot kernels: just what their resident CTAs need, the rest of the 256 KB stays
-    // L1 for their local memory (CSG hit lists, spills).  Measured on 3d_room: 19.6 ms with the driver's default split,
+namespace {
+template <typename K>
+cudaError_t configure_one(K kernel, size_t smem, int resident_ctas) {
+    // Shared-memory carveout: just what the kernel's resident CTAs need, the rest of the 256 KB stays L1 for
+    // local memory (CSG hit lists, spills).  Measured on 3d_room: 19.6 ms with the driver's default split,
     // 19.3 ms at 25 %, 21.3 ms at 100 %.  A hint only; EUCL_CARVEOUT (percent) overrides.
-    {
-        int dev = 0, max_smem_sm = 228 * 1024;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        const size_t need = (size_t)(kResidentThreads / kBlock) * (smem_bytes + 2048);
-        int pct = (int)((need * 100 + (size_t)max_smem_sm - 1) / (size_t)max_smem_sm);
-        if (const char* c = getenv("EUCL_CARVEOUT")) pct = atoi(c);
-        pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
-        cudaFuncSetAttribute(k_intersect<3>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_intersect<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_shade<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_shade<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_shade<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_shade<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
-    if (smem_bytes <= 48 * 1024) return cudaSuccess;
-    const int v = (int)smem_bytes;
+    int dev = 0, max_smem_sm = 228 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    const size_t need = (size_t)resident_ctas * (smem + 2048);
+    int pct = (int)((need * 100 + (size_t)max_smem_sm - 1) / (size_t)max_smem_sm);
+    if (const char* c = getenv("EUCL_CARVEOUT")) pct = atoi(c);
+    pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+} // namespace
+
+cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene) {
     cudaError_t e;
-#define EUCL_SET_SMEM(K) \
-    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, v)) != cudaSuccess) return e
-    EUCL_SET_SMEM(k_camera_entity<3>);
-    EUCL_SET_SMEM(k_camera_entity<4>);
-    EUCL_SET_SMEM(k_raygen<3>);
-    EUCL_SET_SMEM(k_raygen<4>);
-    EUCL_SET_SMEM(k_intersect<3>);
-    EUCL_SET_SMEM(k_intersect<4>);
-    EUCL_SET_SMEM((k_shade<3, true>));
-    EUCL_SET_SMEM((k_shade<4, true>));
-    EUCL_SET_SMEM((k_shade<3, false>));
-    EUCL_SET_SMEM((k_shade<4, false>));
-    EUCL_SET_SMEM(k_megakernel<3>);
-    EUCL_SET_SMEM(k_megakernel<4>);
-    EUCL_SET_SMEM(k_trace_path<3>);
-    EUCL_SET_SMEM(k_trace_path<4>);
-#undef EUCL_SET_SMEM
+    const int heavy = kResidentThreads / kBlock;
+#define EUCL_CONF(K, SMEM, CTAS) \
+    if ((e = configure_one(K, SMEM, CTAS)) != cudaSuccess) return e
+    EUCL_CONF(k_camera_entity<3>, smem_scene, 1);
+    EUCL_CONF(k_camera_entity<4>, smem_scene, 1);
+    EUCL_CONF(k_raygen<3>, smem_scene, 2);
+    EUCL_CONF(k_raygen<4>, smem_scene, 2);
+    EUCL_CONF((k_intersect<3, false>), smem_bytes, heavy);
+    EUCL_CONF((k_intersect<4, false>), smem_bytes, heavy);
+    const size_t smem_light = smem_scene + sizeof(double) * kPlaneChainMax * kLightBlock;
+    EUCL_CONF((k_intersect<3, true>), smem_light, EUCL_INTERSECT_LIGHT_MIN_BLOCKS);
+    EUCL_CONF((k_intersect<4, true>), smem_light, EUCL_INTERSECT_LIGHT_MIN_BLOCKS);
+    EUCL_CONF((k_shade<3, true, true>), smem_scene, heavy);
+    EUCL_CONF((k_shade<4, true, true>), smem_scene, heavy);
+    EUCL_CONF((k_shade<3, false, true>), smem_scene, heavy);
+    EUCL_CONF((k_shade<4, false, true>), smem_scene, heavy);
+    EUCL_CONF((k_shade<3, true, false>), smem_scene, kLightResidentBlocks);
+    EUCL_CONF((k_shade<4, true, false>), smem_scene, kLightResidentBlocks);
+    EUCL_CONF((k_shade<3, false, false>), smem_scene, kLightResidentBlocks);
+    EUCL_CONF((k_shade<4, false, false>), smem_scene, kLightResidentBlocks);
+    EUCL_CONF(k_megakernel<3>, smem_bytes, heavy);
+    EUCL_CONF(k_megakernel<4>, smem_bytes, heavy);
+    EUCL_CONF(k_trace_path<3>, smem_bytes, 1);
+    EUCL_CONF(k_trace_path<4>, smem_bytes, 1);
+#undef EUCL_CONF
     return cudaSuccess;
 }
 

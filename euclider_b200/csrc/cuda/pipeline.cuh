@@ -40,11 +40,16 @@ __host__ __device__ inline int frame_row_of_local(const ChunkParams& c, int loca
     return (k * c.band_world + c.band_rank) * c.band_rows + local_row % c.band_rows;
 }
 
-// What the intersect kernel reports besides the hit point and normal.
-struct __align__(16) HitInfo {
-    int32_t entity;  // hit entity or -1
-    int32_t exiting; // angle_between(direction, normal) < pi/2 (mod.rs:117)
+// What the intersect kernel reports about a ray: the compact hit (parametric distance, primitive, stream
+// flags) from which the shade kernel recomputes location and normal with the intersector's own expressions
+// (intersect.cuh: hit_geometry), plus the orientation of the hit.  32 bytes = one DRAM sector per node.
+struct __align__(16) HitRec {
+    double t;        // parametric distance of the winning hit (the ray direction is not necessarily unit)
     double cos_raw;  // dot(d, n) / (|d| |n|) for the intersector's normal: shading derives its angles from it
+    int32_t entity;  // hit entity or -1
+    int32_t prim;    // primitive the hit lies on
+    int32_t flags;   // CHit flags: bit 0 second root of the primitive, bit 1 normal negated (Complement / SymDiff)
+    int32_t exiting; // angle_between(direction, normal) < pi/2 (mod.rs:117)
 };
 
 // Ray-tree node record written by the shade kernel and consumed by the bottom-up resolve.
@@ -64,29 +69,30 @@ enum : uint32_t {
 
 // Node arena shared by all levels of one chunk: level l occupies node ids
 // [level_off[l], level_off[l] + count[l]).  Rays, hits, metadata and resolved colours are all
-// indexed by node id.  Planes of double2 give 128-bit coalesced loads/stores.
+// indexed by node id.  Every record is an array-of-structures entry made of whole 16-byte words
+// (128-bit accesses) that starts on a 16-byte boundary: the kernels reach most records through index
+// lists (bins), and a gathered node then costs 2 + 1 + 1 DRAM sectors (ray, hit, current entity)
+// where per-component planes cost one half-used sector per plane.
 struct Workspace {
     int32_t capacity;   // nodes
-    int32_t _pad;
-    double2* ray_od;    // D planes of `capacity`: plane k = components (2k, 2k+1) of [origin, direction]
+    int32_t list_cap;   // entries per index list = the largest level the lists can hold
+    double* ray;        // [capacity][2 * D]: origin, direction
     int32_t* ray_cur;   // entity the ray travels in; -1 = no ray (checkerboard pixel)
-    double2* hit_pn;    // D planes: [location, raw normal]
-    HitInfo* hit_ei;    // hit entity or -1, exiting, cos(direction, raw normal): one 128-bit access
+    HitRec* hit;
     NodeMeta* meta;
-    double2* res_rg;    // resolved colour, (r, g)
-    double2* res_ba;    // (b, a)
+    double* res;        // [capacity][4]: resolved colour r, g, b, a (one 32-byte sector)
     int32_t* count;     // [EUCL_MAX_LEVELS + 1] nodes per level
     int32_t* level_off; // [EUCL_MAX_LEVELS + 1] first node id of each level
-    int32_t* overflow;  // set when a child could not be appended
+    int32_t* overflow;  // 1: a child could not be appended (arena); 3: a level outgrew the index lists; 2: internal error
     int32_t* cam_entity; // material_at(camera location), -1 if none
     int32_t n_bins;      // 1: shade in node order; else kBinsPerEntity * n_entities + 1 bins keyed by (hit entity, class), 0 = miss
     int32_t _pad2;
     int32_t* bin_count;  // [EUCL_MAX_LEVELS + 1][kMaxBins] nodes per (level, hit-entity bin)
-    int32_t* order;      // [n_bins][capacity] node ids of the current level grouped by bin (reused per level)
-    int32_t ray_bins;    // 1: the rays of levels >= 1 are walked grouped by reach key (see SceneHeader::cull_root)
+    int32_t* order;      // [n_bins][list_cap] node ids of the current level grouped by bin (reused per level)
+    int32_t ray_bins;    // 1: the rays of a level are walked grouped by reach key (see SceneHeader::cull_root)
     int32_t _pad3;
     int32_t* rbin_count; // [EUCL_MAX_LEVELS + 1][kRayBins]
-    int32_t* rorder;     // [kRayBins][capacity] node ids of the NEXT level grouped by reach key
+    int32_t* rorder;     // [kRayBins][list_cap] node ids of the NEXT level grouped by reach key
     unsigned long long* undefined_count;   // nodes that touched a corner the reference leaves undefined
     unsigned long long* mega_level_counts; // [EUCL_MAX_LEVELS + 1] nodes per level, megakernel pipeline only
 };
@@ -94,9 +100,15 @@ struct Workspace {
 struct Launch {
     cudaStream_t stream;
     const uint8_t* blob;
-    size_t smem_bytes;
-    int grid_max; // blocks of the compute-bound queue kernels (k_intersect, k_shade): resident CTAs per SM x waves
-    int grid_mem; // blocks of the memory-bound kernels (k_raygen, k_resolve, k_final, 256 threads each)
+    size_t smem_bytes; // staged scene + the per-thread plane_chain scratch of a kBlock-thread CTA (k_intersect, k_megakernel, k_trace_path)
+    size_t smem_scene; // staged scene only (the other kernels)
+    int grid_max;   // blocks of the heavy queue kernels (k_intersect, k_shade<GLASS>): resident CTAs per SM x SMs, one wave
+    int grid_light; // blocks of the light shade kernel (kLightBlock threads each), one wave
+    int grid_mem;   // blocks of the memory-bound kernels (k_raygen, k_resolve, k_final, 256 threads each)
+    unsigned long long shade_light_mask, shade_heavy_mask; // shade bins of the light / heavy build of k_shade
+    int grid_light_k2;  // blocks of the light intersect kernel, one wave
+    int light_capable;  // SceneHeader::light_capable
+    int n_cull;         // SceneHeader::n_cull
 };
 
 #ifndef EUCL_BLOCK
@@ -104,6 +116,18 @@ struct Launch {
 #endif
 constexpr int kBlock = EUCL_BLOCK;          // threads per CTA of the scene-walking kernels
 constexpr int kResidentThreads = 512;       // per SM at 128 registers per thread (k_intersect, k_shade)
+#ifndef EUCL_LIGHT_BLOCK
+#define EUCL_LIGHT_BLOCK 256
+#endif
+#ifndef EUCL_SHADE_LIGHT_MIN_BLOCKS
+#define EUCL_SHADE_LIGHT_MIN_BLOCKS 3
+#endif
+constexpr int kLightBlock = EUCL_LIGHT_BLOCK; // threads per CTA of the light shade kernel
+constexpr int kLightResidentBlocks = EUCL_SHADE_LIGHT_MIN_BLOCKS; // ... and CTAs per SM its register budget allows
+#ifndef EUCL_INTERSECT_LIGHT_MIN_BLOCKS
+#define EUCL_INTERSECT_LIGHT_MIN_BLOCKS 3
+#endif
+constexpr int kLightK2ResidentBlocks = EUCL_INTERSECT_LIGHT_MIN_BLOCKS;
 constexpr int kRayBins = 16; // 2^4 reach keys
 constexpr int kBinsPerEntity = 3; // entering, exiting, exiting with total internal reflection predicted
 constexpr int kMaxBins = 64; // shade-coherence bins (miss, then kBinsPerEntity per entity); larger scenes shade unbinned
@@ -112,16 +136,16 @@ constexpr int kMaxBins = 64; // shade-coherence bins (miss, then kBinsPerEntity 
 void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws);
 void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                    int32_t* hit_ids_out);
-void launch_intersect(int dim, const Launch& l, const Workspace& ws, int level);
-void launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
-                  int32_t* hit_ids_out);
+int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level); // returns the number of kernels launched
+int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
+                 int32_t* hit_ids_out); // returns the number of kernels launched (light and / or heavy build)
 void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level);
 void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                   uint8_t* out_rgb8);
 void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                        uint8_t* out_rgb8, int32_t* hit_ids_out);
 void launch_trace_path(int dim, const Launch& l, const double* d_in, double distance, double* d_out, int* d_found);
-cudaError_t configure_kernels(size_t smem_bytes);
+cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene);
 int fp64_peak(double* dadd, double* dmul, double* dfma); // T op/s on the current device
 
 } // namespace eucl

@@ -31,7 +31,17 @@ struct SceneHeader {
     // that own a bounding sphere and are not a bare primitive); used to group the rays of a level
     int32_t n_cull;
     int32_t cull_root[4];
-    int32_t _pad2[3];
+    int32_t off_ent_flags; // per entity: EntFlags
+    int32_t light_capable; // 1: every surfaced entity is a primitive, a root plane chain or a cull root (see k_intersect<LIGHT>)
+    int32_t _pad2[1];
+};
+
+// Per-entity classification for the closest-hit loops (built by eucl_scene_create)
+enum EntFlags : int32_t {
+    ENT_SURFACED = 1,   // takes part in trace_closest
+    ENT_PRIM = 2,       // the shape is one primitive
+    ENT_ROOT_PLANES = 4, // the shape is one chain of <= kPlaneChainMax half-spaces
+    ENT_CULL_ROOT = 8   // owns a reach-key bit: rays with key 0 cannot hit it
 };
 static_assert(sizeof(SceneHeader) % 16 == 0, "header must keep 16-byte alignment");
 
@@ -54,7 +64,7 @@ struct SceneView {
     int dim, n_prims, n_nodes, n_entities, n_surfaces, background;
     int n_cull, cull_root[4];
     uint32_t o_prim_kind, o_prim_v0, o_prim_v1, o_prim_s0, o_prim_s1, o_planes, o_nodes, o_entities, o_materials,
-        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin, o_bounds;
+        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin, o_bounds, o_ent_flags;
 #if defined(__CUDACC__)
 #define EUCL_TABLE(type, name) \
     __device__ __forceinline__ const type* name() const { return reinterpret_cast<const type*>(g_smem + o_##name); }
@@ -76,6 +86,7 @@ struct SceneView {
     EUCL_TABLE(cudaTextureObject_t, tex_objects)
     EUCL_TABLE(uint8_t, perlin)
     EUCL_TABLE(Bound, bounds) // one per macro CSG node
+    EUCL_TABLE(int32_t, ent_flags)
 #undef EUCL_TABLE
 #endif
 };
@@ -125,6 +136,7 @@ __device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restric
         view->o_tex_objects = base + h->off_tex_objects;
         view->o_perlin = base + h->off_perlin;
         view->o_bounds = base + h->off_bounds;
+        view->o_ent_flags = base + h->off_ent_flags;
     }
     __syncthreads();
     return *view;

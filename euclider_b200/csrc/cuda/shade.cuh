@@ -442,11 +442,11 @@ __device__ __forceinline__ double cached_asin(RefractionCache& rc, double arg) {
     return rc.asin_value;
 }
 
-template <int D>
+template <int D, bool GLASS = true>
 __device__ __forceinline__ double reflection_ratio(const EuclSurface& sf, double from_theta, bool exiting,
                                                    RefractionCache& rc) {
     // from_theta = angle_between(direction, -normal_closer), computed once per hit
-    if (sf.ratio_op == EUCL_RATIO_UNIFORM) return exiting ? 0.0 : sf.ratio_a;
+    if (!GLASS || sf.ratio_op == EUCL_RATIO_UNIFORM) return exiting ? 0.0 : sf.ratio_a;
     const double from_index = exiting ? sf.ratio_a : sf.ratio_b;
     const double to_index = exiting ? sf.ratio_b : sf.ratio_a;
     const double to_theta = cached_asin(rc, (from_index / to_index) * rc.sin_from);
@@ -466,10 +466,10 @@ __device__ __forceinline__ Vec<D> reflection_direction(const Vec<D>& dir, const 
 }
 
 // threshold_direction_identity / threshold_direction_snell (surface.rs:259-288)
-template <int D>
+template <int D, bool GLASS = true>
 __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& normal_closer,
                                                       bool exiting, double from_theta, RefractionCache& rc) {
-    if (sf.thr_op == EUCL_THR_IDENTITY) return dir;
+    if (!GLASS || sf.thr_op == EUCL_THR_IDENTITY) return dir;
     const Vec<D> normal = -normal_closer;
     const double modifier = exiting ? sf.thr_a : 1.0 / sf.thr_a;
     const double to_theta = cached_asin(rc, modifier * rc.sin_from);

@@ -276,7 +276,7 @@ typedef struct EuclStats {
     uint32_t levels;
     uint32_t retries;  /* queue-capacity retries taken inside this call */
     uint32_t launches; /* kernels launched by this call */
-    uint32_t _pad;
+    uint32_t ray_grouping; /* 1: this frame walked its rays grouped by reach key (auto-tuned per scene, EUCL_BIN_RAYS forces) */
     float ms_total;     /* device time of the whole call (CUDA events on the render stream) */
     float ms_raygen, ms_intersect, ms_shade, ms_resolve; /* per kernel family */
 } EuclStats;
@@ -298,7 +298,10 @@ uint32_t eucl_band_rows_for_rank(const EuclRenderOpts* opts);
 
 /* Environment::render with HOST output buffers (row 0 = bottom, RGB8, 3*w*rows bytes;
  * hit ids int32 per pixel: entity index of the primary hit, -1 background, -2 checkerboard).
- * Synchronous.  out_hit_ids and stats may be NULL. */
+ * Synchronous.  out_hit_ids and stats may be NULL.
+ * Band-split renders (band_world > 1) with compact_rows == 0 write ONLY this rank's rows of the full-frame
+ * buffer and touch nothing else: N processes, one per GPU, may pass the same shared (ideally pinned) host
+ * frame and fill it over their own PCIe links at the same time. */
 int eucl_render(EuclScene* scene, const EuclCamera* camera, const EuclRenderOpts* opts,
                 uint8_t* out_rgb8, int32_t* out_hit_ids, EuclStats* stats);
 
@@ -337,6 +340,12 @@ int eucl_camera_rotate_plane4(EuclCamera* camera, int axis_a, int axis_b, double
  * tensors out of large pools cannot guarantee. */
 int eucl_device_malloc(int device, uint64_t bytes, void** d_ptr);
 int eucl_device_free(int device, void* d_ptr);
+
+/* Page-locks / unlocks caller-owned host memory (cudaHostRegister, portable) so that eucl_render's copies into it
+ * run at full PCIe speed; meant for frame buffers the caller cannot allocate pinned itself, e.g. one frame in shared
+ * memory that the ranks of a band-split render fill together. */
+int eucl_host_register(void* ptr, uint64_t bytes);
+int eucl_host_unregister(void* ptr);
 
 /* Cross-process frame buffer sharing for the multi-GPU gather (one process per GPU):
  * rank 0 exports its device frame buffer, the other ranks map it and render straight into it. */
