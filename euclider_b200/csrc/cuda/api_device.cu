@@ -498,6 +498,51 @@ struct MacroBuilder {
     }
 };
 
+// LinearSpace expressions in table form (scene_dev.cuh: LinRow): recognises RPN programs of the shape
+//   term (term (+|-))*   with   term := VAR | VAR CONST (*|/) | CONST VAR (*|/)
+// which is how the host compiler (csrc/host/expr.cc) lays out `x * 4`, `4 * x`, `x / 4`, `y`, `x * 2 + y - z / 3`.
+// `in[var]` reads a component of the transformation's input, exactly like EUCL_EX_VAR.
+LinRow lower_lin_row(const EuclExprOp* ops, int len, int dim) {
+    LinRow row{};
+    if (!env_int("EUCL_LIN_TABLE", 1)) return row;
+    int i = 0, n = 0;
+    auto parse_term = [&](LinTerm* out) -> bool {
+        if (i >= len) return false;
+        const EuclExprOp& a = ops[i];
+        if (a.op == EUCL_EX_VAR) {
+            if (a.arg < 0 || a.arg >= dim) return false;
+            if (i + 2 < len && ops[i + 1].op == EUCL_EX_CONST && (ops[i + 2].op == EUCL_EX_MUL || ops[i + 2].op == EUCL_EX_DIV)) {
+                *out = LinTerm{a.arg, ops[i + 2].op == EUCL_EX_MUL ? 1 : 2, ops[i + 1].value};
+                i += 3;
+            } else {
+                *out = LinTerm{a.arg, 0, 0.0};
+                i += 1;
+            }
+            return true;
+        }
+        if (a.op == EUCL_EX_CONST && i + 2 < len && ops[i + 1].op == EUCL_EX_VAR &&
+            (ops[i + 2].op == EUCL_EX_MUL || ops[i + 2].op == EUCL_EX_DIV)) {
+            if (ops[i + 1].arg < 0 || ops[i + 1].arg >= dim) return false;
+            *out = LinTerm{ops[i + 1].arg, ops[i + 2].op == EUCL_EX_MUL ? 1 : 3, a.value}; // c * v == v * c in IEEE arithmetic
+            i += 3;
+            return true;
+        }
+        return false;
+    };
+    LinTerm t{};
+    if (!parse_term(&t)) return LinRow{};
+    row.t[n++] = t;
+    while (i < len) {
+        if (n >= kLinTermsMax || !parse_term(&t)) return LinRow{};
+        if (i >= len || (ops[i].op != EUCL_EX_ADD && ops[i].op != EUCL_EX_SUB)) return LinRow{};
+        if (ops[i].op == EUCL_EX_SUB) t.kind |= 16;
+        ++i;
+        row.t[n++] = t;
+    }
+    row.n_terms = n;
+    return row;
+}
+
 struct BlobWriter {
     std::vector<uint8_t> bytes;
     int reserve(size_t n) {
@@ -703,6 +748,14 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     h.off_materials = w.put(flat->materials, (size_t)flat->n_materials);
     h.off_transforms = w.put(flat->transforms, (size_t)flat->n_transforms);
     h.off_expr_ops = w.put(flat->expr_ops, (size_t)flat->n_expr_ops);
+    std::vector<LinRow> lin_rows((size_t)std::max(flat->n_transforms, 1) * 2 * EUCL_MAX_DIM);
+    for (int t = 0; t < flat->n_transforms; ++t)
+        for (int k = 0; k < flat->dim; ++k) {
+            const EuclTransform& tr = flat->transforms[t];
+            lin_rows[(size_t)t * 2 * EUCL_MAX_DIM + k] = lower_lin_row(flat->expr_ops + tr.fwd_first[k], tr.fwd_len[k], flat->dim);
+            lin_rows[(size_t)t * 2 * EUCL_MAX_DIM + EUCL_MAX_DIM + k] = lower_lin_row(flat->expr_ops + tr.inv_first[k], tr.inv_len[k], flat->dim);
+        }
+    h.off_lin_rows = w.put(lin_rows.data(), lin_rows.size());
     h.off_surfaces = w.put(flat->surfaces, (size_t)flat->n_surfaces);
     h.off_color_ops = w.put(flat->color_ops, (size_t)flat->n_color_ops);
     h.off_mapped = w.put(flat->mapped_textures, (size_t)flat->n_mapped_textures);
@@ -792,7 +845,8 @@ void frame_params(const EuclCamera& cam, const EuclRenderOpts& o, FrameParams* f
 }
 
 size_t arena_bytes(int dim, size_t cap) {
-    size_t per = (size_t)dim * 16 + 4 + sizeof(HitRec) + sizeof(NodeMeta) + 32;
+    const size_t hit_bytes = (size_t)kHitDoubles * 8;
+    size_t per = (size_t)dim * 16 + 4 + hit_bytes + sizeof(NodeMeta) + 32;
     return per * cap + 16 * 16;
 }
 
@@ -807,7 +861,7 @@ Workspace carve(EuclScene* s, int dim, int cap, int list_cap) {
         return r;
     };
     ws.ray = (double*)take((size_t)dim * 16 * cap);
-    ws.hit = (HitRec*)take(sizeof(HitRec) * (size_t)cap);
+    ws.hit = (double*)take((size_t)kHitDoubles * 8 * (size_t)cap);
     ws.res = (double*)take((size_t)32 * cap);
     ws.meta = (NodeMeta*)take(sizeof(NodeMeta) * (size_t)cap);
     ws.ray_cur = (int32_t*)take((size_t)4 * cap);
@@ -860,6 +914,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene,
                  s->sm_count * std::max(1, env_int("EUCL_BLOCKS_PER_SM", kResidentThreads / kBlock)),
                  s->sm_count * std::max(1, env_int("EUCL_LIGHT_BLOCKS_PER_SM", kLightResidentBlocks)),
+                 s->sm_count * std::max(1, env_int("EUCL_SHADE_BLOCKS_PER_SM", kShadeResidentBlocks)),
                  s->sm_count * std::max(1, env_int("EUCL_MEM_BLOCKS_PER_SM", 8)),
                  s->shade_light_mask, s->shade_heavy_mask,
                  s->sm_count * std::max(1, env_int("EUCL_LIGHT_K2_BLOCKS_PER_SM", kLightK2ResidentBlocks)), s->light_capable, s->n_cull};
@@ -1156,7 +1211,7 @@ int eucl_trace_path(EuclScene* s, const double* location, const double* directio
         h_in[D + k] = direction[k];
     }
     EUCL_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, s->stream));
-    Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene, 1, 1, 1, 1ull, 0ull, 1, 0, 0};
+    Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene, 1, 1, 1, 1, 1ull, 0ull, 1, 0, 0};
     launch_trace_path(D, l, d_in, distance, d_out, d_found);
     double h_out[2 * EUCL_MAX_DIM];
     int h_found = 0;

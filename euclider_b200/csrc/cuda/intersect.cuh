@@ -143,7 +143,7 @@ __device__ __forceinline__ bool chain_inside(const SceneView& sv, int op, int p0
 // ComposableShape::is_point_inside (shape.rs:587-601) of macro node `n`: a bit stack over the
 // macro post-order range (all operands are pure, so no short-circuit is needed between siblings).
 template <int D>
-__device__ __noinline__ bool node_inside(const SceneView& sv, int n, const Vec<D>& p) {
+__device__ __noinline__ bool node_inside(const SceneView& sv, int n, EUCL_VARG(Vec<D>) p) {
     const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes());
     const MNode root = mn[n];
     if (root.kind == M_PRIM) return prim_inside<D>(sv, root.a, p);
@@ -174,7 +174,7 @@ __device__ __noinline__ bool node_inside(const SceneView& sv, int n, const Vec<D
 
 // Universe::material_at (mod.rs:229-251): first entity in list order containing the point
 template <int D>
-__device__ __noinline__ int material_at(const SceneView& sv, const Vec<D>& p) {
+__device__ __noinline__ int material_at(const SceneView& sv, EUCL_VARG(Vec<D>) p) {
     for (int e = 0; e < sv.n_entities; ++e) {
         const int root = sv.entities()[e].node_root;
         // a point outside the (inflated) bounding sphere of the shape cannot be inside it; NaN -> not skipped

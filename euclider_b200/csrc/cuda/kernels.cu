@@ -20,9 +20,6 @@ namespace {
 #ifndef EUCL_INTERSECT_MIN_BLOCKS
 #define EUCL_INTERSECT_MIN_BLOCKS (kResidentThreads / kBlock)
 #endif
-#ifndef EUCL_SHADE_MIN_BLOCKS
-#define EUCL_SHADE_MIN_BLOCKS (kResidentThreads / kBlock)
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // node arena access (array-of-structures records made of 128-bit words)
@@ -56,17 +53,34 @@ __device__ __forceinline__ void load_ray(const Workspace& ws, int node, Vec<D>& 
         d[k] = v[D + k];
     }
 }
-__device__ __forceinline__ void store_hit(const Workspace& ws, int node, const HitRec& h) {
-    double2* rec = reinterpret_cast<double2*>(ws.hit + node);
-    rec[0] = make_double2(h.t, h.cos_raw);
-    int4 w = make_int4(h.entity, h.prim, h.flags, h.exiting);
-    reinterpret_cast<int4*>(rec)[1] = w;
+template <int D>
+__device__ __forceinline__ void store_hit(const Workspace& ws, int node, const HitHead& h, const Vec<D>& n) {
+    constexpr int K = kHitDoubles;
+    double v[K];
+    v[0] = h.t;
+    v[1] = h.cos_raw;
+    v[2] = __hiloint2double(h.exiting, h.entity); // low word = entity, high word = exiting
+    v[3] = h.angle_raw;
+#pragma unroll
+    for (int k = 4; k < K; ++k) v[k] = k - 4 < D ? n[k - 4 < D ? k - 4 : 0] : 0.0;
+    double2* rec = reinterpret_cast<double2*>(ws.hit + (size_t)node * K);
+#pragma unroll
+    for (int k = 0; k < K / 2; ++k) rec[k] = make_double2(v[2 * k], v[2 * k + 1]);
 }
-__device__ __forceinline__ HitRec load_hit(const Workspace& ws, int node) {
-    const double2* rec = reinterpret_cast<const double2*>(ws.hit + node);
-    const double2 a = rec[0];
-    const int4 w = reinterpret_cast<const int4*>(rec)[1];
-    return HitRec{a.x, a.y, w.x, w.y, w.z, w.w};
+template <int D>
+__device__ __forceinline__ HitHead load_hit(const Workspace& ws, int node, Vec<D>& n) {
+    constexpr int K = kHitDoubles;
+    const double2* rec = reinterpret_cast<const double2*>(ws.hit + (size_t)node * K);
+    double v[K];
+#pragma unroll
+    for (int k = 0; k < (4 + D + 1) / 2; ++k) {
+        const double2 w = rec[k];
+        v[2 * k] = w.x;
+        v[2 * k + 1] = w.y;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) n[k] = v[4 + k];
+    return HitHead{v[0], v[1], v[3], __double2loint(v[2]), __double2hiint(v[2])};
 }
 __device__ __forceinline__ void store_res(const Workspace& ws, int node, const Rgba& c) {
     double2* rec = reinterpret_cast<double2*>(ws.res + (size_t)node * 4);
@@ -93,12 +107,13 @@ __device__ __forceinline__ double* plane_scratch(const uint8_t* __restrict__ blo
 // and its orientation relative to the ray (mod.rs:114-125).
 template <int D>
 __device__ __forceinline__ int intersect_ray(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, bool& exiting, Vec<D>& p,
-                                             Vec<D>& n_raw, double& cos_raw, double* ts, int ts_stride) {
+                                             Vec<D>& n_raw, double& cos_raw, double& angle_raw, double* ts, int ts_stride) {
     const ClosestHit h = closest_hit<D>(sv, o, d, ts, ts_stride);
     if (h.entity < 0) return -1;
     hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n_raw);
     cos_raw = angle_cos(d, n_raw);
-    exiting = angle_from_cos(cos_raw) < kFracPi2;
+    angle_raw = angle_from_cos(cos_raw);
+    exiting = angle_raw < kFracPi2;
     return h.entity;
 }
 
@@ -117,58 +132,105 @@ struct ShadeOut {
     ChildRay<D> t, r;
 };
 
-// ComposableSurface::get_color up to (not including) the recursive trace calls
-// (surface.rs:62-162): decides which children exist and where they start.
+// ComposableSurface::get_color up to (not including) the recursive trace calls (surface.rs:62-162), in two steps so
+// that the wavefront kernel can reserve the children's slots between them and build each child ray only when it is
+// about to store it (the two rays are 4 * D doubles that would otherwise stay live across the whole shading code).
+//
+// Step 1, shade_decide: reflection ratio, surface colour and its u8 quantisation, and WHICH children exist.
 // GLASS = false compiles the Fresnel / Snell providers out: the light shade kernel only ever sees surfaces
 // with a uniform reflection ratio and the identity threshold direction (the host routes the bins).
+template <int D>
+struct ShadeDecision {
+    double ratio;
+    unsigned q;
+    unsigned flags;
+    bool t_emit, r_emit;
+    int dest;          // entity the transmitted ray continues in (valid when t_emit)
+    double from_theta; // angle_between(direction, -normal_closer); Fresnel / Snell surfaces only
+    RefractionCache rc;
+};
 template <int D, bool GLASS>
-__device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
-                                          bool exiting, double cos_raw, const Vec<D>& p, const Vec<D>& n_raw,
-                                          ShadeOut<D>& out) {
+__device__ __forceinline__ void shade_decide(const SceneView& sv, double time_millis, int ent, bool exiting, double cos_raw,
+                                             double angle_raw, const Vec<D>& p, const Vec<D>& n_raw, ShadeDecision<D>& out,
+                                             Rgba& sc_out) {
     const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
-    const Vec<D> n_closer = exiting ? -n_raw : n_raw;
     const double cos_closer = exiting ? -cos_raw : cos_raw;
     const bool needs_theta = GLASS && (sf.ratio_op == EUCL_RATIO_FRESNEL || sf.thr_op == EUCL_THR_SNELL);
-    const double from_theta = needs_theta ? angle_from_cos(-cos_closer) : 0.0;
-    RefractionCache rc{needs_theta ? dm_sin(from_theta) : 0.0, 0.0, 0.0, false};
+    // angle_between(direction, -normal_closer): when exiting, -normal_closer IS the raw normal and the angle is the stored one
+#if EUCL_ANGLE_REUSE
+    out.from_theta = needs_theta ? (exiting ? angle_raw : angle_from_cos(-cos_closer)) : 0.0;
+#else
+    out.from_theta = needs_theta ? angle_from_cos(-cos_closer) : 0.0;
+#endif
+    out.rc = RefractionCache{needs_theta ? dm_sin(out.from_theta) : 0.0, 0.0, 0.0, false};
     // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
-    const double ratio = fmax(fmin(reflection_ratio<D, GLASS>(sf, from_theta, exiting, rc), 1.0), 0.0);
+    const double ratio = fmax(fmin(reflection_ratio<D, GLASS>(sf, out.from_theta, exiting, out.rc), 1.0), 0.0);
     out.ratio = ratio;
     out.q = 0u;
     out.flags = 0u;
     out.t_emit = false;
-    out.r_emit = false;
+    out.dest = -1;
     bool have_t = false;
     if (!(ratio >= 1.0)) { // get_intersection_color
-        const Rgba sc = surface_color<D>(sv, sf, dir, p, n_raw, cos_raw, cos_closer, time_millis);
+        const Rgba sc = surface_color<D>(sv, sf, p, n_raw, cos_raw, angle_raw, exiting, time_millis);
         const unsigned q = to_pixel4(sc);
         out.q = q;
         if ((q >> 24) == 255u) {
-            out.sc = sc;
+            sc_out = sc;
             out.flags |= NODE_HAS_SC;
             have_t = true;
         } else {
-            Vec<D> td = threshold_direction<D, GLASS>(sf, dir, n_closer, exiting, from_theta, rc);
-            const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
-            const int dest = exiting ? material_at<D>(sv, new_origin) : ent;
+            int dest = ent;
+            if (exiting) {
+                const Vec<D> n_closer = -n_raw;
+                dest = material_at<D>(sv, p + (-n_closer) * kApproxEpsilon * 128.0);
+            }
             if (dest >= 0) {
-                material_exit<D>(sv, cur, td);
-                material_enter<D>(sv, dest, td);
                 out.t_emit = true;
-                out.t.o = new_origin;
-                out.t.d = td;
-                out.t.cur = dest;
+                out.dest = dest;
                 have_t = true;
             }
         }
     }
-    if (!(ratio <= 0.0)) { // get_reflection_color
-        out.r_emit = true;
-        out.r.o = p + n_closer * kApproxEpsilon * 128.0;
-        out.r.d = reflection_direction<D>(dir, n_closer);
-        out.r.cur = cur;
-    }
+    out.r_emit = !(ratio <= 0.0); // get_reflection_color
     if (!have_t && !out.r_emit) out.flags |= NODE_UNDEFINED | NODE_LEAF;
+}
+// Step 2: the child rays (surface.rs:84-100 transmitted, :119-139 reflected).
+template <int D, bool GLASS>
+__device__ __forceinline__ void transmit_child(const SceneView& sv, const Vec<D>& dir, int cur, int ent, bool exiting, const Vec<D>& p,
+                                               const Vec<D>& n_raw, ShadeDecision<D>& dec, ChildRay<D>& out) {
+    const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
+    const Vec<D> n_closer = exiting ? -n_raw : n_raw;
+    Vec<D> td = threshold_direction<D, GLASS>(sf, dir, n_closer, exiting, dec.from_theta, dec.rc);
+    out.o = p + (-n_closer) * kApproxEpsilon * 128.0;
+    material_exit<D>(sv, cur, td);
+    material_enter<D>(sv, dec.dest, td);
+    out.d = td;
+    out.cur = dec.dest;
+}
+template <int D>
+__device__ __forceinline__ void reflect_child(const Vec<D>& dir, int cur, bool exiting, const Vec<D>& p, const Vec<D>& n_raw,
+                                              ChildRay<D>& out) {
+    const Vec<D> n_closer = exiting ? -n_raw : n_raw;
+    out.o = p + n_closer * kApproxEpsilon * 128.0;
+    out.d = reflection_direction<D>(dir, n_closer);
+    out.cur = cur;
+}
+
+// Both steps at once (megakernel, which keeps the children on its own stack).
+template <int D, bool GLASS>
+__device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
+                                          bool exiting, double cos_raw, double angle_raw, const Vec<D>& p, const Vec<D>& n_raw,
+                                          ShadeOut<D>& out) {
+    ShadeDecision<D> dec;
+    shade_decide<D, GLASS>(sv, time_millis, ent, exiting, cos_raw, angle_raw, p, n_raw, dec, out.sc);
+    out.ratio = dec.ratio;
+    out.q = dec.q;
+    out.flags = dec.flags;
+    out.t_emit = dec.t_emit;
+    out.r_emit = dec.r_emit;
+    if (dec.t_emit) transmit_child<D, GLASS>(sv, dir, cur, ent, exiting, p, n_raw, dec, out.t);
+    if (dec.r_emit) reflect_child<D>(dir, cur, exiting, p, n_raw, out.r);
 }
 
 // Colour of an inner node from its children (surface.rs:104-114,150-161)
@@ -276,7 +338,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
 // evaluator and its per-thread hit arena, at a fraction of the registers; the HEAVY one walks the other keys (or every
 // ray when the level is not grouped).  `key_mask` selects the reach-key lists of a launch.
 template <int D, bool LIGHT>
-__global__ void __launch_bounds__(LIGHT ? kLightBlock : kBlock, LIGHT ? EUCL_INTERSECT_LIGHT_MIN_BLOCKS : EUCL_INTERSECT_MIN_BLOCKS)
+__global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_INTERSECT_LIGHT_MIN_BLOCKS : EUCL_INTERSECT_MIN_BLOCKS)
     k_intersect(const uint8_t* __restrict__ blob, Workspace ws, int level, unsigned key_mask) {
     // an earlier level did not fit: the host grows the arena and retries.  One decision per block (see k_shade).
     __shared__ int s_skip, s_total;
@@ -328,18 +390,22 @@ __global__ void __launch_bounds__(LIGHT ? kLightBlock : kBlock, LIGHT ? EUCL_INT
             Vec<D> o, d;
             load_ray<D>(ws, node, o, d);
             const ClosestHit h = LIGHT ? closest_hit_light<D>(sv, o, d, ts, (int)blockDim.x) : closest_hit<D>(sv, o, d, ts, (int)blockDim.x);
-            HitRec rec{0.0, 0.0, -1, 0, 0, 0};
+            HitHead rec{0.0, 0.0, 0.0, -1, 0};
+            Vec<D> n;
+#pragma unroll
+            for (int k = 0; k < D; ++k) n[k] = 0.0;
             if (h.entity >= 0) { // orientation of the winner relative to the ray (mod.rs:114-125)
-                Vec<D> p, n;
+                Vec<D> p;
                 hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n);
                 const double cos_raw = angle_cos(d, n);
-                const bool exiting = angle_from_cos(cos_raw) < kFracPi2;
-                rec = HitRec{h.t, cos_raw, h.entity, h.prim, h.flags, exiting ? 1 : 0};
+                const double angle_raw = angle_from_cos(cos_raw);
+                const bool exiting = angle_raw < kFracPi2;
+                rec = HitHead{h.t, cos_raw, angle_raw, h.entity, exiting ? 1 : 0};
                 exiting_flag = exiting;
                 cos_hint = cos_raw;
             }
             ent = h.entity;
-            store_hit(ws, node, rec);
+            store_hit<D>(ws, node, rec, n);
         }
         if (ws.n_bins > 1) {
             // group the level's nodes by hit entity so that a shading warp runs ONE surface program:
@@ -378,7 +444,7 @@ __global__ void __launch_bounds__(LIGHT ? kLightBlock : kBlock, LIGHT ? EUCL_INT
 // and keeps more warps resident.  The HEAVY one (GLASS = true) shades the remaining bins (and everything when the
 // level is not binned).  `bin_mask` selects the bins of a launch.
 template <int D, bool RAY_BINS, bool GLASS>
-__global__ void __launch_bounds__(GLASS ? kBlock : kLightBlock, GLASS ? EUCL_SHADE_MIN_BLOCKS : EUCL_SHADE_LIGHT_MIN_BLOCKS)
+__global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUCL_SHADE_MIN_BLOCKS : EUCL_SHADE_LIGHT_MIN_BLOCKS)
     k_shade(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp, Workspace ws, int level, unsigned long long bin_mask,
             int32_t* __restrict__ hit_ids_out) {
     const int off = ws.level_off[level], cnt = ws.count[level];
@@ -435,14 +501,15 @@ __global__ void __launch_bounds__(GLASS ? kBlock : kLightBlock, GLASS ? EUCL_SHA
             valid = cur >= 0; // checkerboard pixels carry no ray
         }
         const int i = node - off;
-        ShadeOut<D> so;
-        so.t_emit = false;
-        so.r_emit = false;
+        ShadeDecision<D> dec;
+        dec.t_emit = false;
+        dec.r_emit = false;
         bool shaded = false;
         if (valid) {
-            Vec<D> o, d;
+            Vec<D> o, d, n;
             load_ray<D>(ws, node, o, d);
-            const HitRec ei = last_level ? HitRec{0.0, 0.0, -1, 0, 0, 0} : load_hit(ws, node);
+            HitHead ei{0.0, 0.0, 0.0, -1, 0};
+            if (!last_level) ei = load_hit<D>(ws, node, n);
             if (level == 0 && hit_ids_out) {
                 const int local_row = cp.local_row0 + i / fp.width;
                 const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
@@ -452,15 +519,22 @@ __global__ void __launch_bounds__(GLASS ? kBlock : kLightBlock, GLASS ? EUCL_SHA
                 store_res(ws, node, mapped_color<D>(sv, sv.background, d)); // background.get_color(direction.to_point())
                 ws.meta[node] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF};
             } else {
-                Vec<D> p, n; // location and normal as the intersector reports them, from the compact hit
-                hit_geometry<D>(sv, ei.prim, ei.flags, o, d, ei.t, p, n);
-                shade_hit<D, GLASS>(sv, fp.time_millis, d, cur, ei.entity, ei.exiting != 0, ei.cos_raw, p, n, so);
+                const Vec<D> p = o + d * ei.t; // the intersectors' expression for the hit location (shape.rs:700,795,993)
+                Rgba sc;
+                shade_decide<D, GLASS>(sv, fp.time_millis, ei.entity, ei.exiting != 0, ei.cos_raw, ei.angle_raw, p, n, dec, sc);
+                if (dec.flags & NODE_HAS_SC) {
+                    store_res(ws, node, sc);
+                    if (!dec.r_emit) dec.flags |= NODE_LEAF; // opaque without a mirror term: the colour is final
+                }
+                if (dec.flags & NODE_UNDEFINED) {
+                    store_res(ws, node, Rgba{0.0, 0.0, 0.0, 0.0});
+                    atomicAdd(ws.undefined_count, 1ull);
+                }
                 shaded = true;
             }
         }
-        int so_tchild = -1, so_rchild = -1;
         // warp-aggregated append of the children to level + 1: one atomicAdd per warp
-        const unsigned tmask = __ballot_sync(0xffffffffu, so.t_emit), rmask = __ballot_sync(0xffffffffu, so.r_emit);
+        const unsigned tmask = __ballot_sync(0xffffffffu, dec.t_emit), rmask = __ballot_sync(0xffffffffu, dec.r_emit);
         const int nt = __popc(tmask), n_children = nt + __popc(rmask);
         int slot = 0;
         if (n_children > 0) {
@@ -470,38 +544,40 @@ __global__ void __launch_bounds__(GLASS ? kBlock : kLightBlock, GLASS ? EUCL_SHA
         const bool fits_arena = (long long)next_off + slot + n_children <= (long long)ws.capacity;
         const bool fits = n_children > 0 && fits_arena && slot + n_children <= ws.list_cap; // the index lists hold one level each
         if (n_children > 0 && !fits && lane == 0) *ws.overflow = fits_arena ? 3 : 1;
+        int tchild = -1, rchild = -1, tkey = 0, rkey = 0;
         if (shaded) {
-            const unsigned lt = (1u << lane) - 1u;
-            int tchild = -1, rchild = -1;
-            if (fits && so.t_emit) {
-                tchild = next_off + slot + __popc(tmask & lt);
-                store_ray<D>(ws, tchild, so.t.o, so.t.d, so.t.cur);
+            if (fits && (dec.t_emit || dec.r_emit)) {
+                // The child rays need the ray and the hit again.  They are re-read from the node arena (L2-hot: this thread
+                // loaded them a few microseconds ago) instead of being kept in ~40 registers across the whole shading code;
+                // the loads are issued while the slot reservation above is still in flight.
+                Vec<D> o, d, n;
+                load_ray<D>(ws, node, o, d);
+                const HitHead ei = load_hit<D>(ws, node, n);
+                const Vec<D> p = o + d * ei.t;
+                const bool exiting = ei.exiting != 0;
+                const unsigned lt = (1u << lane) - 1u;
+                ChildRay<D> child; // one child at a time: built, stored, forgotten
+                if (dec.t_emit) {
+                    tchild = next_off + slot + __popc(tmask & lt);
+                    transmit_child<D, GLASS>(sv, d, cur, ei.entity, exiting, p, n, dec, child);
+                    store_ray<D>(ws, tchild, child.o, child.d, child.cur);
+                    if (RAY_BINS) tkey = reach_key<D>(sv, child.o, child.d);
+                }
+                if (dec.r_emit) {
+                    rchild = next_off + slot + nt + __popc(rmask & lt);
+                    reflect_child<D>(d, cur, exiting, p, n, child);
+                    store_ray<D>(ws, rchild, child.o, child.d, child.cur);
+                    if (RAY_BINS) rkey = reach_key<D>(sv, child.o, child.d);
+                }
             }
-            if (fits && so.r_emit) {
-                rchild = next_off + slot + nt + __popc(rmask & lt);
-                store_ray<D>(ws, rchild, so.r.o, so.r.d, so.r.cur);
-            }
-            so_tchild = tchild;
-            so_rchild = rchild;
-            unsigned flags = so.flags;
-            if (flags & NODE_HAS_SC) {
-                store_res(ws, node, so.sc);
-                if (!so.r_emit) flags |= NODE_LEAF; // opaque without a mirror term: the colour is final
-            }
-            if (flags & NODE_UNDEFINED) {
-                store_res(ws, node, Rgba{0.0, 0.0, 0.0, 0.0});
-                atomicAdd(ws.undefined_count, 1ull);
-            }
-            ws.meta[node] = NodeMeta{so.ratio, tchild, rchild, so.q, flags};
+            ws.meta[node] = NodeMeta{dec.ratio, tchild, rchild, dec.q, dec.flags};
         }
         if (RAY_BINS) {
-            // group the NEXT level's rays by reach key (one atomicAdd per warp and distinct key, twice:
-            // transmitted children, then reflected ones).  Called with the members of `so` directly: choosing
-            // between so.t and so.r through a reference would force both into local memory.
-            auto bin_child = [&](int child, const Vec<D>& co, const Vec<D>& cd) {
+            // group the NEXT level's rays by reach key: one atomicAdd per warp and distinct key, for the transmitted
+            // children and then for the reflected ones
+            auto bin_child = [&](int child, int key) {
                 const unsigned active = __ballot_sync(0xffffffffu, child >= 0);
                 if (child >= 0) {
-                    const int key = reach_key<D>(sv, co, cd);
                     const unsigned peers = __match_any_sync(active, key);
                     const int leader = __ffs(peers) - 1;
                     int s2 = 0;
@@ -510,8 +586,8 @@ __global__ void __launch_bounds__(GLASS ? kBlock : kLightBlock, GLASS ? EUCL_SHA
                     ws.rorder[(size_t)key * ws.list_cap + s2 + __popc(peers & ((1u << lane) - 1u))] = child;
                 }
             };
-            bin_child(so_tchild, so.t.o, so.t.d);
-            bin_child(so_rchild, so.r.o, so.r.d);
+            bin_child(tchild, tkey);
+            bin_child(rchild, rkey);
         }
     }
 }
@@ -619,14 +695,14 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
             int ent = -1;
             bool exiting = false;
             Vec<D> p, n;
-            double cos_raw = 0.0;
-            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, ts, (int)blockDim.x);
+            double cos_raw = 0.0, angle_raw = 0.0;
+            if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, angle_raw, ts, (int)blockDim.x);
             if (level == 0 && hit_ids_out) hit_ids_out[opix] = ent;
             if (ent < 0) {
                 val = mapped_color<D>(sv, sv.background, d);
             } else {
                 ShadeOut<D> so;
-                shade_hit<D, true>(sv, fp.time_millis, d, cur, ent, exiting, cos_raw, p, n, so);
+                shade_hit<D, true>(sv, fp.time_millis, d, cur, ent, exiting, cos_raw, angle_raw, p, n, so);
                 if (so.flags & NODE_UNDEFINED) {
                     val = Rgba{0.0, 0.0, 0.0, 0.0};
                     atomicAdd(ws.undefined_count, 1ull);
@@ -809,11 +885,11 @@ int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
     // a light-capable scene without cull roots (every ray has key 0) runs the light build in node order
     const bool light_all = l.light_capable && l.n_cull == 0;
     const bool split = l.light_capable && ws.ray_bins != 0;
-    const size_t smem_light = l.smem_scene + sizeof(double) * kPlaneChainMax * kLightBlock;
+    const size_t smem_light = l.smem_scene + sizeof(double) * kPlaneChainMax * kLightK2Block;
     int launches = 0;
     if (light_all || split) {
-        EUCL_DISPATCH_DIM(dim, (k_intersect<3, true><<<l.grid_light_k2, kLightBlock, smem_light, l.stream>>>(l.blob, ws, level, 1u)),
-                          (k_intersect<4, true><<<l.grid_light_k2, kLightBlock, smem_light, l.stream>>>(l.blob, ws, level, 1u)));
+        EUCL_DISPATCH_DIM(dim, (k_intersect<3, true><<<l.grid_light_k2, kLightK2Block, smem_light, l.stream>>>(l.blob, ws, level, 1u)),
+                          (k_intersect<4, true><<<l.grid_light_k2, kLightK2Block, smem_light, l.stream>>>(l.blob, ws, level, 1u)));
         ++launches;
     }
     if (!light_all) {
@@ -827,7 +903,7 @@ int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
 template <int D, bool RAY_BINS, bool GLASS>
 static void launch_shade_one(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
                              unsigned long long mask, int32_t* hit_ids_out) {
-    if (GLASS) k_shade<D, RAY_BINS, true><<<l.grid_max, kBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
+    if (GLASS) k_shade<D, RAY_BINS, true><<<l.grid_shade, kShadeBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
     else k_shade<D, RAY_BINS, false><<<l.grid_light, kLightBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
 }
 template <int D, bool GLASS>
@@ -912,13 +988,13 @@ cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene) {
     EUCL_CONF(k_raygen<4>, smem_scene, 2);
     EUCL_CONF((k_intersect<3, false>), smem_bytes, heavy);
     EUCL_CONF((k_intersect<4, false>), smem_bytes, heavy);
-    const size_t smem_light = smem_scene + sizeof(double) * kPlaneChainMax * kLightBlock;
+    const size_t smem_light = smem_scene + sizeof(double) * kPlaneChainMax * kLightK2Block;
     EUCL_CONF((k_intersect<3, true>), smem_light, EUCL_INTERSECT_LIGHT_MIN_BLOCKS);
     EUCL_CONF((k_intersect<4, true>), smem_light, EUCL_INTERSECT_LIGHT_MIN_BLOCKS);
-    EUCL_CONF((k_shade<3, true, true>), smem_scene, heavy);
-    EUCL_CONF((k_shade<4, true, true>), smem_scene, heavy);
-    EUCL_CONF((k_shade<3, false, true>), smem_scene, heavy);
-    EUCL_CONF((k_shade<4, false, true>), smem_scene, heavy);
+    EUCL_CONF((k_shade<3, true, true>), smem_scene, kShadeResidentBlocks);
+    EUCL_CONF((k_shade<4, true, true>), smem_scene, kShadeResidentBlocks);
+    EUCL_CONF((k_shade<3, false, true>), smem_scene, kShadeResidentBlocks);
+    EUCL_CONF((k_shade<4, false, true>), smem_scene, kShadeResidentBlocks);
     EUCL_CONF((k_shade<3, true, false>), smem_scene, kLightResidentBlocks);
     EUCL_CONF((k_shade<4, true, false>), smem_scene, kLightResidentBlocks);
     EUCL_CONF((k_shade<3, false, false>), smem_scene, kLightResidentBlocks);

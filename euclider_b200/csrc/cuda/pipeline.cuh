@@ -40,16 +40,19 @@ __host__ __device__ inline int frame_row_of_local(const ChunkParams& c, int loca
     return (k * c.band_world + c.band_rank) * c.band_rows + local_row % c.band_rows;
 }
 
-// What the intersect kernel reports about a ray: the compact hit (parametric distance, primitive, stream
-// flags) from which the shade kernel recomputes location and normal with the intersector's own expressions
-// (intersect.cuh: hit_geometry), plus the orientation of the hit.  32 bytes = one DRAM sector per node.
-struct __align__(16) HitRec {
-    double t;        // parametric distance of the winning hit (the ray direction is not necessarily unit)
-    double cos_raw;  // dot(d, n) / (|d| |n|) for the intersector's normal: shading derives its angles from it
-    int32_t entity;  // hit entity or -1
-    int32_t prim;    // primitive the hit lies on
-    int32_t flags;   // CHit flags: bit 0 second root of the primitive, bit 1 normal negated (Complement / SymDiff)
-    int32_t exiting; // angle_between(direction, normal) < pi/2 (mod.rs:117)
+// What the intersect kernel reports about a ray, one array-of-structures record of kHitDoubles doubles per node:
+//   [0] t          parametric distance of the winning hit (the ray direction is not necessarily unit)
+//   [1] cos_raw    dot(d, n) / (|d| |n|) for the intersector's normal: shading derives its angles from it
+//   [2] (entity, exiting) as two int32: hit entity or -1; angle_between(direction, normal) < pi/2 (mod.rs:117)
+//   [3] angle_raw  angle_between(direction, normal) = acos(cos_raw), NaN -> 0: evaluated here for `exiting`, reused by the
+//                  illumination / Fresnel / Snell providers whenever they ask for the angle of this same cosine
+//   [4 .. 4 + D)   the intersector's normal
+// The hit location is not stored: o + d * t from the ray record is the intersectors' own expression for it.
+// 64 bytes (3-D: one pad double): four 128-bit words, two whole DRAM sectors per gathered node.
+constexpr int kHitDoubles = 8;
+struct HitHead {
+    double t, cos_raw, angle_raw;
+    int32_t entity, exiting;
 };
 
 // Ray-tree node record written by the shade kernel and consumed by the bottom-up resolve.
@@ -78,7 +81,7 @@ struct Workspace {
     int32_t list_cap;   // entries per index list = the largest level the lists can hold
     double* ray;        // [capacity][2 * D]: origin, direction
     int32_t* ray_cur;   // entity the ray travels in; -1 = no ray (checkerboard pixel)
-    HitRec* hit;
+    double* hit;        // [capacity][kHitDoubles]
     NodeMeta* meta;
     double* res;        // [capacity][4]: resolved colour r, g, b, a (one 32-byte sector)
     int32_t* count;     // [EUCL_MAX_LEVELS + 1] nodes per level
@@ -104,6 +107,7 @@ struct Launch {
     size_t smem_scene; // staged scene only (the other kernels)
     int grid_max;   // blocks of the heavy queue kernels (k_intersect, k_shade<GLASS>): resident CTAs per SM x SMs, one wave
     int grid_light; // blocks of the light shade kernel (kLightBlock threads each), one wave
+    int grid_shade; // blocks of the heavy shade kernel (kShadeBlock threads each), one wave
     int grid_mem;   // blocks of the memory-bound kernels (k_raygen, k_resolve, k_final, 256 threads each)
     unsigned long long shade_light_mask, shade_heavy_mask; // shade bins of the light / heavy build of k_shade
     int grid_light_k2;  // blocks of the light intersect kernel, one wave
@@ -120,13 +124,25 @@ constexpr int kResidentThreads = 512;       // per SM at 128 registers per threa
 #define EUCL_LIGHT_BLOCK 256
 #endif
 #ifndef EUCL_SHADE_LIGHT_MIN_BLOCKS
-#define EUCL_SHADE_LIGHT_MIN_BLOCKS 3
+#define EUCL_SHADE_LIGHT_MIN_BLOCKS 2 /* 3d_room 4K, shade ms per frame: 3 CTAs of 256 (80 registers, 370 B of spills) 8.50; 5 of 128 (96) 8.03; 4 of 128 / 2 of 256 (128 registers, no spills) 7.29 / 7.16 */
 #endif
+#ifndef EUCL_SHADE_BLOCK
+#define EUCL_SHADE_BLOCK EUCL_BLOCK
+#endif
+#ifndef EUCL_SHADE_MIN_BLOCKS
+#define EUCL_SHADE_MIN_BLOCKS (512 / EUCL_SHADE_BLOCK > 0 ? 512 / EUCL_SHADE_BLOCK : 1)
+#endif
+constexpr int kShadeBlock = EUCL_SHADE_BLOCK; // threads per CTA of the heavy shade kernel
+constexpr int kShadeResidentBlocks = EUCL_SHADE_MIN_BLOCKS;
 constexpr int kLightBlock = EUCL_LIGHT_BLOCK; // threads per CTA of the light shade kernel
 constexpr int kLightResidentBlocks = EUCL_SHADE_LIGHT_MIN_BLOCKS; // ... and CTAs per SM its register budget allows
-#ifndef EUCL_INTERSECT_LIGHT_MIN_BLOCKS
-#define EUCL_INTERSECT_LIGHT_MIN_BLOCKS 3
+#ifndef EUCL_LIGHT_K2_BLOCK
+#define EUCL_LIGHT_K2_BLOCK 128
 #endif
+#ifndef EUCL_INTERSECT_LIGHT_MIN_BLOCKS
+#define EUCL_INTERSECT_LIGHT_MIN_BLOCKS 5 /* 640 threads per SM at 95 registers, no spills */
+#endif
+constexpr int kLightK2Block = EUCL_LIGHT_K2_BLOCK; // threads per CTA of the light intersect kernel
 constexpr int kLightK2ResidentBlocks = EUCL_INTERSECT_LIGHT_MIN_BLOCKS;
 constexpr int kRayBins = 16; // 2^4 reach keys
 constexpr int kBinsPerEntity = 3; // entering, exiting, exiting with total internal reflection predicted

@@ -33,8 +33,27 @@ struct SceneHeader {
     int32_t cull_root[4];
     int32_t off_ent_flags; // per entity: EntFlags
     int32_t light_capable; // 1: every surfaced entity is a primitive, a root plane chain or a cull root (see k_intersect<LIGHT>)
-    int32_t _pad2[1];
+    int32_t off_lin_rows;  // LinRow table, 2 * EUCL_MAX_DIM rows per transform
 };
+
+// LinearSpace in table form.  eucl_scene_create recognises component expressions that are sums of terms
+//   v | v * c | c * v | v / c      (v a legend variable, c a literal; terms joined by + or -, left to right)
+// -- the hallway stretch `x * 4`, its inverse `x / 4`, pass-through `y` -- and lowers each to a row of at most
+// kLinTermsMax terms.  A row performs exactly the IEEE operations meval's evaluation of the expression performs, in
+// the same order, so results are bit-identical to the RPN interpreter, which stays as the fallback (n_terms == 0).
+constexpr int kLinTermsMax = 4;
+struct LinTerm {
+    int32_t var;  // component of the INPUT vector
+    int32_t kind; // 0: v, 1: v * c, 2: v / c, 3: c / v; bit 4 set: the term is subtracted from the running sum
+    double c;
+};
+struct LinRow {
+    int32_t n_terms; // 0: not a recognised row, evaluate the RPN program
+    int32_t _pad;
+    LinTerm t[kLinTermsMax];
+};
+static_assert(sizeof(LinRow) % 8 == 0, "LinRow alignment");
+// rows of transform t: [t * 2 * EUCL_MAX_DIM + (inverse ? EUCL_MAX_DIM : 0) + component]
 
 // Per-entity classification for the closest-hit loops (built by eucl_scene_create)
 enum EntFlags : int32_t {
@@ -64,7 +83,7 @@ struct SceneView {
     int dim, n_prims, n_nodes, n_entities, n_surfaces, background;
     int n_cull, cull_root[4];
     uint32_t o_prim_kind, o_prim_v0, o_prim_v1, o_prim_s0, o_prim_s1, o_planes, o_nodes, o_entities, o_materials,
-        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin, o_bounds, o_ent_flags;
+        o_transforms, o_expr_ops, o_surfaces, o_color_ops, o_mapped, o_textures, o_tex_objects, o_perlin, o_bounds, o_ent_flags, o_lin_rows;
 #if defined(__CUDACC__)
 #define EUCL_TABLE(type, name) \
     __device__ __forceinline__ const type* name() const { return reinterpret_cast<const type*>(g_smem + o_##name); }
@@ -87,6 +106,7 @@ struct SceneView {
     EUCL_TABLE(uint8_t, perlin)
     EUCL_TABLE(Bound, bounds) // one per macro CSG node
     EUCL_TABLE(int32_t, ent_flags)
+    EUCL_TABLE(LinRow, lin_rows)
 #undef EUCL_TABLE
 #endif
 };
@@ -137,6 +157,7 @@ __device__ __forceinline__ const SceneView& stage_scene(const uint8_t* __restric
         view->o_perlin = base + h->off_perlin;
         view->o_bounds = base + h->off_bounds;
         view->o_ent_flags = base + h->off_ent_flags;
+        view->o_lin_rows = base + h->off_lin_rows;
     }
     __syncthreads();
     return *view;

@@ -85,7 +85,7 @@ __device__ __forceinline__ double blend_channel(int fn, double a, double b, doub
 }
 
 // palette Blend on premultiplied colours: `s` = self (source), `d` = argument (destination)
-__device__ __noinline__ Pre blend_pre(int fn, const Pre& s, const Pre& d) {
+__device__ __noinline__ Pre blend_pre(int fn, EUCL_VARG(Pre) s, EUCL_VARG(Pre) d) {
     const double sa = s.a, da = d.a;
     double alpha;
     switch (fn) {
@@ -96,8 +96,12 @@ __device__ __noinline__ Pre blend_pre(int fn, const Pre& s, const Pre& d) {
     case EUCL_BLEND_PLUS: alpha = clamp01(sa + da); break;
     default: alpha = clamp01(sa + da - sa * da); break;
     }
-    return Pre{blend_channel(fn, s.r, d.r, sa, da), blend_channel(fn, s.g, d.g, sa, da),
-               blend_channel(fn, s.b, d.b, sa, da), alpha};
+    // one rolled loop over the colour channels: a single copy of the 17-way switch in the kernel's code
+    const double sc[3] = {s.r, s.g, s.b}, dc[3] = {d.r, d.g, d.b};
+    double out[3];
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) out[k] = blend_channel(fn, sc[k], dc[k], sa, da);
+    return Pre{out[0], out[1], out[2], alpha};
 }
 __device__ __forceinline__ Pre over_pre(const Pre& s, const Pre& d) {
     return Pre{s.r + d.r * (1.0 - s.a), s.g + d.g * (1.0 - s.a), s.b + d.b * (1.0 - s.a),
@@ -134,7 +138,8 @@ __device__ __forceinline__ Rgba hue_to_rgba(double hue_degrees) {
 }
 
 // noise 0.4.1 Perlin::get([f64; 4]) with the seed-0 permutation table staged in shared memory
-__device__ __noinline__ double perlin4(const uint8_t* perm, const double point[4]) {
+__device__ __noinline__ double perlin4(const uint8_t* perm, double px, double py, double pz, double pw) {
+    const double point[4] = {px, py, pz, pw};
     const double diag = 0.577350269189625764077083524672081875;
     double near_d[4], far_d[4];
     long long near_c[4];
@@ -216,7 +221,7 @@ __device__ __forceinline__ Rgba fetch_texel(cudaTextureObject_t tex, const EuclT
 
 // MappedTextureImpl::get_color with uv_sphere (+ uv_derank in 4-D) and the two image filters
 template <int D>
-__device__ __noinline__ Rgba mapped_color(const SceneView& sv, int mapped, const Vec<D>& point) {
+__device__ __noinline__ Rgba mapped_color(const SceneView& sv, int mapped, EUCL_VARG(Vec<D>) point) {
     if (mapped < 0) return Rgba{0.0, 0.0, 0.0, 0.0}; // MappedTextureTransparent
     const EuclMappedTexture mt = sv.mapped()[mapped];
     Vec<3> p;
@@ -309,36 +314,53 @@ __device__ __noinline__ double eval_expr(const SceneView& sv, int first, int len
 }
 
 // ComponentTransformation::transform_with (material.rs:91-112): all component expressions see the
-// same input vector
+// same input vector.  Components lowered to table rows (scene_dev.cuh: LinRow) run as a few multiplications /
+// divisions / additions; anything else goes through the RPN interpreter.
 template <int D>
-__device__ __noinline__ void apply_transform(const SceneView& sv, const EuclTransform& t, bool inverse, Vec<D>& v) {
+__device__ __noinline__ void apply_transform(const SceneView& sv, int t_index, bool inverse, Vec<D>& v) {
+    const EuclTransform& t = sv.transforms()[t_index];
+    const LinRow* rows = sv.lin_rows() + (size_t)t_index * 2 * EUCL_MAX_DIM + (inverse ? EUCL_MAX_DIM : 0);
     double in[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) in[k] = v[k];
 #pragma unroll
-    for (int k = 0; k < D; ++k)
-        v[k] = inverse ? eval_expr(sv, t.inv_first[k], t.inv_len[k], in) : eval_expr(sv, t.fwd_first[k], t.fwd_len[k], in);
+    for (int k = 0; k < D; ++k) {
+        const LinRow& row = rows[k];
+        if (row.n_terms == 0) {
+            v[k] = inverse ? eval_expr(sv, t.inv_first[k], t.inv_len[k], in) : eval_expr(sv, t.fwd_first[k], t.fwd_len[k], in);
+            continue;
+        }
+        double acc = 0.0;
+        for (int j = 0; j < row.n_terms; ++j) {
+            const LinTerm term = row.t[j];
+            const double x = in[term.var];
+            const int kind = term.kind & 15;
+            const double val = kind == 0 ? x : kind == 1 ? x * term.c : kind == 2 ? x / term.c : term.c / x;
+            acc = j == 0 ? val : ((term.kind & 16) ? acc - val : acc + val);
+        }
+        v[k] = acc;
+    }
 }
 // Material::enter (Vacuum: no-op, material.rs:43-49; LinearSpace: forward transforms in order, :133-137)
 template <int D>
 __device__ __forceinline__ void material_enter(const SceneView& sv, int entity, Vec<D>& dir) {
     const EuclMaterial m = sv.materials()[sv.entities()[entity].material];
     if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
-    for (int k = 0; k < m.n_transforms; ++k) apply_transform<D>(sv, sv.transforms()[m.transform_first + k], false, dir);
+    for (int k = 0; k < m.n_transforms; ++k) apply_transform<D>(sv, m.transform_first + k, false, dir);
 }
 // Material::exit (LinearSpace: inverse transforms in reverse order, material.rs:139-142,156-162)
 template <int D>
 __device__ __forceinline__ void material_exit(const SceneView& sv, int entity, Vec<D>& dir) {
     const EuclMaterial m = sv.materials()[sv.entities()[entity].material];
     if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
-    for (int k = m.n_transforms - 1; k >= 0; --k) apply_transform<D>(sv, sv.transforms()[m.transform_first + k], true, dir);
+    for (int k = m.n_transforms - 1; k >= 0; --k) apply_transform<D>(sv, m.transform_first + k, true, dir);
 }
 
 // --- surface providers -------------------------------------------------------------------------
 
 // util.rs:631-666: rotate `v` in the plane spanned by (self_, other) by `angle`
 template <int D>
-__device__ __noinline__ Vec<D> general_rotation(const Vec<D>& self_, const Vec<D>& other, double angle, const Vec<D>& v) {
+__device__ __noinline__ Vec<D> general_rotation(EUCL_VARG(Vec<D>) self_, EUCL_VARG(Vec<D>) other, double angle, EUCL_VARG(Vec<D>) v) {
     double original[D][D], result[D][D]; // [row][col]
 #pragma unroll
     for (int r = 0; r < D; ++r)
@@ -479,8 +501,31 @@ __device__ __forceinline__ Vec<D> threshold_direction(const EuclSurface& sf, con
 
 // The surface colour program (postfix) of surface `sf` at a hit.
 template <int D>
-__device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& dir, const Vec<D>& location,
-                                     const Vec<D>& normal_raw, double cos_raw, double cos_closer, double time_millis) {
+#ifndef EUCL_INLINE_SURFACE_COLOR
+#define EUCL_INLINE_SURFACE_COLOR 1 /* one call site per kernel; inlined: 3d_room shade 7.45 -> 7.14 ms, 4d_room 4.48 -> 4.26 */
+#endif
+#ifndef EUCL_ANGLE_REUSE
+#define EUCL_ANGLE_REUSE 1
+#endif
+#if EUCL_INLINE_SURFACE_COLOR
+#define EUCL_SC_INLINE __forceinline__
+#else
+#define EUCL_SC_INLINE __noinline__
+#endif
+__device__ EUCL_SC_INLINE Rgba surface_color(const SceneView& sv, const EuclSurface& sf, const Vec<D>& location,
+                                     const Vec<D>& normal_raw, double cos_raw, double angle_raw_in, bool exiting, double time_millis) {
+    // angle_raw = angle_between(direction, raw normal), evaluated by the intersect kernel; the angle to normal_closer is the
+    // same number when entering and acos of the negated cosine when exiting (computed at most once per program)
+#if EUCL_ANGLE_REUSE
+    const double angle_raw = angle_raw_in;
+    double angle_closer = angle_raw;
+    bool have_closer = !exiting;
+#else
+    const double angle_raw = angle_from_cos(cos_raw);
+    double angle_closer = 0.0;
+    bool have_closer = false;
+    (void)angle_raw_in;
+#endif
     Rgba stack[kColorStackMax];
     int sp = 0;
     for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
@@ -491,7 +536,11 @@ __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurfac
         } else if (code == EUCL_COL_ILLUM_GLOBAL) { // surface.rs:410-422
             const Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
             // angle_between(normal_closer, direction): same products and norms as (direction, normal_closer)
-            const double original_angle = angle_from_cos(cos_closer);
+            if (!have_closer) {
+                angle_closer = angle_from_cos(exiting ? -cos_raw : cos_raw);
+                have_closer = true;
+            }
+            const double original_angle = angle_closer;
             const double angle = kPi - original_angle;
             const double ratio = angle / kFracPi2;
             stack[sp++] = combine_palette_color(dark, light, ratio);
@@ -501,14 +550,13 @@ __device__ __noinline__ Rgba surface_color(const SceneView& sv, const EuclSurfac
 #pragma unroll
             for (int k = 0; k < D; ++k) light_direction[k] = op.f[8 + k];
             Vec<D> normal = normal_raw;
-            if (angle_from_cos(cos_raw) > kFracPi2) normal = -normal; // angle_between(direction, raw normal)
+            if (angle_raw > kFracPi2) normal = -normal; // angle_between(direction, raw normal)
             const double angle = angle_between(normal, -light_direction);
             const double ratio = 1.0 - angle / kPi;
             stack[sp++] = combine_palette_color(dark, light, ratio);
         } else if (code == EUCL_COL_PERLIN_HUE) { // d3/entity/surface.rs:22-40
             const double size = op.f[0], speed = op.f[1];
-            const double point[4] = {location[0] / size, location[1] / size, location[2] / size, time_millis * speed};
-            stack[sp++] = hue_to_rgba(perlin4(sv.perlin(), point) * 360.0);
+            stack[sp++] = hue_to_rgba(perlin4(sv.perlin(), location[0] / size, location[1] / size, location[2] / size, time_millis * speed) * 360.0);
         } else if (code == EUCL_COL_TEXTURE) { // surface.rs:536-542
             stack[sp++] = mapped_color<D>(sv, op.i0, location);
         } else { // EUCL_COL_BLEND, surface.rs:295-307

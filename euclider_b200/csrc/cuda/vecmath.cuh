@@ -10,6 +10,16 @@
 
 namespace eucl {
 
+// how small vectors / colours are passed to the out-of-line helpers: by value (registers) or by reference (local memory)
+#ifndef EUCL_BYVAL
+#define EUCL_BYVAL 1
+#endif
+#if EUCL_BYVAL
+#define EUCL_VARG(T) const T
+#else
+#define EUCL_VARG(T) const T&
+#endif
+
 template <int D>
 struct Vec {
     double c[D];

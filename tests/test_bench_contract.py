@@ -22,6 +22,20 @@ def test_reference_arm_prints_one_json_line(built_lib, oracle):
     assert d["config"]["workload"].startswith("3d_fresnel 1920x1080")
 
 
+def test_reference_arm_renders_whole_frames_by_default(built_lib, oracle):
+    """Without --ref-rows the reference arm renders every row of every timed frame: ms_per_step is measured, not
+    extrapolated (small frame here so that the CPU suite stays short)."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                        "--scene", "3d_fresnel", "--width", "160", "--height", "90"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert d["steps"] == 3 and d["cpu_baseline"]["sample"] == "whole 160x90 frames"
+    assert "measured" in d["config"]["note"] and d["ms_per_step"] > 0
+    # segments per frame are deterministic: value * time reproduces an integer multiple of one frame's count
+    segs = d["value"] * 1e6 * d["ms_per_step"] * 1e-3
+    assert abs(segs - round(segs)) < 1e-3 * max(1.0, segs)
+
+
 def test_reference_arm_is_silent_on_other_ranks(built_lib, oracle):
     """Under torchrun only rank 0 runs the reference arm; the other ranks exit 0 without work."""
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
