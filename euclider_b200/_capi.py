@@ -97,7 +97,7 @@ class EuclStats(C.Structure):
     _fields_ = [("pixels", C.c_uint64), ("segments", C.c_uint64), ("nodes", C.c_uint64),
                 ("level_counts", C.c_uint64 * EUCL_MAX_LEVELS), ("levels", C.c_uint32), ("retries", C.c_uint32),
                 ("launches", C.c_uint32), ("ray_grouping", C.c_uint32), ("ms_total", C.c_float), ("ms_raygen", C.c_float),
-                ("ms_intersect", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float)]
+                ("ms_intersect", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float), ("graph_replays", C.c_uint32)]
 
 
 # enums (values from the header)

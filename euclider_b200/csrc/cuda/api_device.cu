@@ -70,6 +70,8 @@ struct EuclScene {
     cudaStream_t stream = nullptr;     // the stream kernels run on (own_stream unless the caller set one)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t side_stream = nullptr;                  // light builds of a level's kernels run here, next to the heavy ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> prof_events; // per-launch events, profile mode only
     // workspace (grow-only)
     DeviceBuffer nodes;    // the node arena
@@ -87,12 +89,16 @@ struct EuclScene {
     // does not depend on it.  EUCL_BIN_RAYS=0/1 forces a setting.
     int ray_bins_mode = -1;      // -1 undecided, 0 off, 1 on
     bool ray_bins_now = true;    // setting of the frame being rendered
-    float tune_ms[2] = {0.f, 0.f};
+    float tune_ms[2] = {0.f, 0.f}; // fastest frame seen without / with grouping
+    int tune_count[2] = {0, 0};    // frames measured without / with grouping
     uint64_t tune_pixels = 0;    // frame size the two timings belong to
     int warm_frames = 0;         // frames rendered so far
     int n_entities = 0;
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
+    cudaGraphExec_t graph_exec = nullptr; // the last repeated chunk as a CUDA graph (render_impl)
+    uint64_t graph_key = 0, seen_key = 0; // parameter hash of graph_exec / of the previous direct launch sequence
+    uint32_t graph_launches = 0;
     int list_capacity = 0;     // entries per index list (bins, reach keys): the largest LEVEL a chunk may have
     double list_factor = 1.0;  // ... in nodes per pixel (level 0 has exactly one; deeper levels are smaller in every shipped scene)
     int32_t* h_small = nullptr; // pinned mirror of the counters
@@ -585,10 +591,14 @@ void eucl_scene_destroy(EuclScene* s) {
     s->order.release();
     s->path_io.release();
     s->rorder.release();
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->h_small) cudaFreeHost(s->h_small);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : s->prof_events) cudaEventDestroy(e);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -630,6 +640,9 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     s->stream = s->own_stream;
     EUCL_CUDA_S(cudaEventCreate(&s->ev[0]));
     EUCL_CUDA_S(cudaEventCreate(&s->ev[1]));
+    EUCL_CUDA_S(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+    EUCL_CUDA_S(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    EUCL_CUDA_S(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 
     // textures -> CUDA arrays + point-sampled texture objects
     for (int t = 0; t < flat->n_textures; ++t) {
@@ -895,7 +908,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         const int forced = env_int("EUCL_BIN_RAYS", -1);
         if (forced >= 0) s->ray_bins_mode = forced ? 1 : 0;
         if (s->ray_bins_mode >= 0) s->ray_bins_now = s->ray_bins_mode == 1;
-        else s->ray_bins_now = s->tune_ms[1] == 0.f; // first measure "on", then "off"
+        else s->ray_bins_now = s->tune_count[1] <= s->tune_count[0]; // undecided: alternate, "on" first
     }
     EUCL_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (my_rows > 0) {
@@ -917,7 +930,10 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                  s->sm_count * std::max(1, env_int("EUCL_SHADE_BLOCKS_PER_SM", kShadeResidentBlocks)),
                  s->sm_count * std::max(1, env_int("EUCL_MEM_BLOCKS_PER_SM", 8)),
                  s->shade_light_mask, s->shade_heavy_mask,
-                 s->sm_count * std::max(1, env_int("EUCL_LIGHT_K2_BLOCKS_PER_SM", kLightK2ResidentBlocks)), s->light_capable, s->n_cull};
+                 s->sm_count * std::max(1, env_int("EUCL_LIGHT_K2_BLOCKS_PER_SM", kLightK2ResidentBlocks)), s->light_capable, s->n_cull,
+                 // per-launch profiling and the debugging modes keep everything on one stream
+                 (o->profile || env_int("EUCL_DEBUG_SYNC", 0) || !env_int("EUCL_CONCURRENT", 1)) ? nullptr : s->side_stream, s->ev_fork,
+                 s->ev_join};
         const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
         const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && kBinsPerEntity * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
@@ -976,7 +992,6 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     continue;
                 }
                 Workspace ws = carve(s, dim, s->arena_capacity, s->list_capacity);
-                EUCL_CUDA(cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream));
                 // profile mode: one event after every launch; family = 0 raygen, 1 intersect, 2 shade, 3 resolve
                 std::vector<int> prof_family;
                 auto mark = [&](int family) {
@@ -993,6 +1008,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                 // EUCL_POISON=1: fill the work buffers with 0x7F bytes (huge positive indices) first, so that a read of anything this
                 // frame did not write turns into a deterministic fault instead of depending on stale data
                 const bool debug_sync = env_int("EUCL_DEBUG_SYNC", 0) != 0;
+                const bool poison = env_int("EUCL_POISON", 0) != 0;
                 std::string fault;
                 auto dbg = [&](const char* what, int level) {
                     if (!debug_sync || !fault.empty()) return;
@@ -1000,47 +1016,111 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     if (e == cudaSuccess) e = cudaGetLastError();
                     if (e != cudaSuccess) fault = std::string(what) + " level " + std::to_string(level) + ": " + cudaGetErrorString(e);
                 };
-                if (env_int("EUCL_POISON", 0)) {
-                    cudaMemsetAsync(s->nodes.ptr, 0x7F, s->nodes.bytes, s->stream);
-                    if (s->order.ptr) cudaMemsetAsync(s->order.ptr, 0x7F, s->order.bytes, s->stream);
-                    if (s->rorder.ptr) cudaMemsetAsync(s->rorder.ptr, 0x7F, s->rorder.bytes, s->stream);
-                }
-                mark(-1);
-                launch_camera_entity(dim, l, fp, ws);
-                dbg("k_camera_entity", 0);
-                st.launches += 1;
-                if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) {
-                    if (cam->max_depth > 24) return fail(EUCL_ERR_SCENE_LIMIT, "megakernel pipeline supports max_depth <= 24");
-                    launch_megakernel(dim, l, fp, cp, ws, d_rgb, d_hit);
-                    mark(1);
-                    st.launches += 1;
-                } else {
-                    launch_raygen(dim, l, fp, cp, ws, d_hit);
-                    dbg("k_raygen", 0);
-                    mark(0);
-                    for (int level = 0; level < (int)cam->max_depth; ++level) {
-                        st.launches += launch_intersect(dim, l, ws, level);
-                        dbg("k_intersect", level);
+                if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL && cam->max_depth > 24)
+                    return fail(EUCL_ERR_SCENE_LIMIT, "megakernel pipeline supports max_depth <= 24");
+                // everything one chunk puts on the stream: counters reset, kernels, counters back to the pinned mirror
+                auto enqueue = [&]() -> uint32_t {
+                    uint32_t launches = 0;
+                    cudaMemsetAsync(s->small.ptr, 0, sizeof(int32_t) * kSmallInts, s->stream);
+                    if (poison) {
+                        cudaMemsetAsync(s->nodes.ptr, 0x7F, s->nodes.bytes, s->stream);
+                        if (s->order.ptr) cudaMemsetAsync(s->order.ptr, 0x7F, s->order.bytes, s->stream);
+                        if (s->rorder.ptr) cudaMemsetAsync(s->rorder.ptr, 0x7F, s->rorder.bytes, s->stream);
+                    }
+                    mark(-1);
+                    if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) {
+                        launch_camera_entity(dim, l, fp, ws);
+                        dbg("k_camera_entity", 0);
+                        launch_megakernel(dim, l, fp, cp, ws, d_rgb, d_hit);
                         mark(1);
-                        st.launches += launch_shade(dim, l, fp, cp, ws, level, d_hit);
-                        dbg("k_shade", level);
+                        launches += 2;
+                    } else {
+                        launch_raygen(dim, l, fp, cp, ws, d_hit);
+                        dbg("k_raygen", 0);
+                        mark(0);
+                        for (int level = 0; level < (int)cam->max_depth; ++level) {
+                            launches += launch_intersect(dim, l, ws, level);
+                            dbg("k_intersect", level);
+                            mark(1);
+                            launches += launch_shade(dim, l, fp, cp, ws, level, d_hit);
+                            dbg("k_shade", level);
+                            mark(2);
+                        }
+                        launches += launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
+                        dbg("k_shade", (int)cam->max_depth);
                         mark(2);
+                        for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
+                            launch_resolve(dim, l, ws, level);
+                            dbg("k_resolve", level);
+                        }
+                        launch_final(dim, l, fp, cp, ws, d_rgb);
+                        dbg("k_final", 0);
+                        mark(3);
+                        launches += 2 + (cam->max_depth == 0 ? 0 : cam->max_depth - 1); // raygen, final, resolve levels
                     }
-                    st.launches += launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
-                    dbg("k_shade", (int)cam->max_depth);
-                    mark(2);
-                    for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
-                        launch_resolve(dim, l, ws, level);
-                        dbg("k_resolve", level);
-                    }
-                    launch_final(dim, l, fp, cp, ws, d_rgb);
-                    dbg("k_final", 0);
-                    mark(3);
-                    if (!fault.empty()) return fail(EUCL_ERR_CUDA, "EUCL_DEBUG_SYNC: " + fault);
-                    st.launches += 2 + (cam->max_depth == 0 ? 0 : cam->max_depth - 1); // raygen, final, resolve levels
+                    cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost, s->stream);
+                    return launches;
+                };
+                // A chunk whose launch parameters repeat (a fixed pose rendered again: benchmarks, a paused camera, every rank
+                // of a band-split frame) is replayed as ONE CUDA graph launch: the ~50 kernels of a frame then cost one
+                // driver call on the host and run back to back on the device.  The first sighting of a parameter set
+                // launches directly, the second captures, later ones replay.  EUCL_GRAPH=0 disables.
+                uint64_t key = 1469598103934665603ull;
+                auto mix = [&](const void* data, size_t bytes) {
+                    const unsigned char* b = (const unsigned char*)data;
+                    for (size_t k = 0; k < bytes; ++k) key = (key ^ b[k]) * 1099511628211ull;
+                };
+                mix(&fp, sizeof fp);
+                mix(&cp, sizeof cp);
+                mix(&ws, sizeof ws);
+                {   // the members of Launch one by one (the struct has padding bytes)
+                    const void* ptrs[] = {l.stream, l.blob, l.side};
+                    const unsigned long long nums[] = {l.smem_bytes, l.smem_scene, (unsigned long long)l.grid_max, (unsigned long long)l.grid_light,
+                                                       (unsigned long long)l.grid_shade, (unsigned long long)l.grid_mem, l.shade_light_mask,
+                                                       l.shade_heavy_mask, (unsigned long long)l.grid_light_k2,
+                                                       (unsigned long long)l.light_capable, (unsigned long long)l.n_cull};
+                    mix(ptrs, sizeof ptrs);
+                    mix(nums, sizeof nums);
                 }
-                EUCL_CUDA(cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost,
-                                          s->stream));
+                mix(&d_rgb, sizeof d_rgb);
+                mix(&d_hit, sizeof d_hit);
+                const int pipeline_id = o->pipeline;
+                mix(&pipeline_id, sizeof pipeline_id);
+                const uint32_t depth_id = cam->max_depth;
+                mix(&depth_id, sizeof depth_id);
+                // (not while the scene is still choosing its ray-grouping mode: capture time would distort the comparison)
+                const bool graph_ok = env_int("EUCL_GRAPH", 1) && !o->profile && !debug_sync && !poison &&
+                                      (s->ray_bins_mode >= 0 || o->pipeline != EUCL_PIPELINE_WAVEFRONT);
+                if (graph_ok && s->graph_exec && s->graph_key == key) {
+                    EUCL_CUDA(cudaGraphLaunch(s->graph_exec, s->stream));
+                    st.launches += s->graph_launches;
+                    st.graph_replays += 1;
+                } else if (graph_ok && s->seen_key == key) {
+                    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+                    s->graph_exec = nullptr;
+                    cudaGraph_t graph = nullptr;
+                    EUCL_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+                    const uint32_t launches = enqueue();
+                    cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+                    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+                    if (graph) cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) { // not capturable here (e.g. a caller's stream in a state that forbids it): launch directly
+                        cudaGetLastError();
+                        s->graph_exec = nullptr;
+                        s->seen_key = 0;
+                        st.launches += enqueue();
+                    } else {
+                        s->graph_key = key;
+                        s->graph_launches = launches;
+                        EUCL_CUDA(cudaGraphLaunch(s->graph_exec, s->stream));
+                        st.launches += launches;
+                        st.graph_replays += 1;
+                    }
+                } else {
+                    s->seen_key = key;
+                    st.launches += enqueue();
+                }
+                if (!fault.empty()) return fail(EUCL_ERR_CUDA, "EUCL_DEBUG_SYNC: " + fault);
                 EUCL_CUDA(cudaStreamSynchronize(s->stream));
                 EUCL_CUDA(cudaGetLastError());
                 for (size_t k = 1; k < prof_family.size(); ++k) {
@@ -1106,9 +1186,14 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
             if (s->tune_pixels != st.pixels) { // only frames of one size are comparable
                 s->tune_pixels = st.pixels;
                 s->tune_ms[0] = s->tune_ms[1] = 0.f;
+                s->tune_count[0] = s->tune_count[1] = 0;
             }
-            s->tune_ms[s->ray_bins_now ? 1 : 0] = st.ms_total;
-            if (s->tune_ms[0] > 0.f && s->tune_ms[1] > 0.f) s->ray_bins_mode = s->tune_ms[1] < s->tune_ms[0] ? 1 : 0;
+            // two frames per setting, alternating, the faster one of each counts: one slow frame (another process on
+            // the GPU, a clock ramp) must not decide; EuclStats.ray_grouping reports what a frame used
+            const int m = s->ray_bins_now ? 1 : 0;
+            s->tune_ms[m] = s->tune_count[m] == 0 ? st.ms_total : std::min(s->tune_ms[m], st.ms_total);
+            s->tune_count[m] += 1;
+            if (s->tune_count[0] >= 2 && s->tune_count[1] >= 2) s->ray_bins_mode = s->tune_ms[1] < s->tune_ms[0] ? 1 : 0;
         }
     }
     s->warm_frames++;
@@ -1211,7 +1296,7 @@ int eucl_trace_path(EuclScene* s, const double* location, const double* directio
         h_in[D + k] = direction[k];
     }
     EUCL_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, s->stream));
-    Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene, 1, 1, 1, 1, 1ull, 0ull, 1, 0, 0};
+    Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene, 1, 1, 1, 1, 1ull, 0ull, 1, 0, 0, nullptr, nullptr, nullptr};
     launch_trace_path(D, l, d_in, distance, d_out, d_found);
     double h_out[2 * EUCL_MAX_DIM];
     int h_found = 0;

@@ -93,6 +93,11 @@ __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
     return Rgba{rg.x, rg.y, ba.x, ba.y};
 }
 
+// First queue position of this warp in the grid-stride walk of the queue kernels (CTA-contiguous).  Measured and not kept:
+// handing consecutive 32-entry chunks to different SMs so that the last, partly filled wave of a launch spreads over the
+// whole GPU -- no gain on a full 3d_room frame (15.79 vs 15.59 ms) nor on a 1/8-frame band (2.54 vs 2.50 ms).
+__device__ __forceinline__ int warp_first_position() { return (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); }
+
 // Per-thread scratch column for plane_chain (kPlaneChainMax doubles per thread, element i of thread
 // t at [i * blockDim.x + t]): lives in dynamic shared memory right after the staged scene.
 __device__ __forceinline__ double* plane_scratch(const uint8_t* __restrict__ blob) {
@@ -289,14 +294,22 @@ template <int D>
 __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp,
                                                    Workspace ws, int32_t* __restrict__ hit_ids_out) {
     const SceneView& sv = stage_scene(blob);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        ws.count[0] = cp.n_pixels;
-        ws.level_off[0] = 0;
-    }
-    const int belongs_to = *ws.cam_entity;
     Vec<D> loc;
 #pragma unroll
     for (int k = 0; k < D; ++k) loc[k] = fp.location[k];
+    // material_at(camera location) is the same for every pixel of a frame: one thread per CTA evaluates it (a few hundred
+    // instructions) instead of a kernel of its own in front of this one
+    __shared__ int s_cam_entity;
+    if (threadIdx.x == 0) {
+        s_cam_entity = material_at<D>(sv, loc);
+        if (blockIdx.x == 0) {
+            *ws.cam_entity = s_cam_entity;
+            ws.count[0] = cp.n_pixels;
+            ws.level_off[0] = 0;
+        }
+    }
+    __syncthreads();
+    const int belongs_to = s_cam_entity;
     const unsigned lane = threadIdx.x & 31u;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < cp.n_pixels; base += gridDim.x * blockDim.x) {
         const int i = base + (int)lane;
@@ -362,11 +375,12 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
     }
     __syncthreads();
     const int total = s_total;
-    if (s_skip || blockIdx.x * blockDim.x >= total) return;
+    if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
     const SceneView& sv = stage_scene(blob);
     double* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
+    const int first = warp_first_position();
     int bin = 0; // the lists of a launch are walked front to back: the cursor only moves forward
     auto node_at = [&](int i) -> int {
         if (i >= total) return -1;
@@ -374,8 +388,8 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
         while (i >= s_rprefix[bin + 1]) ++bin;
         return ws.rorder[(size_t)bin * ws.list_cap + (i - s_rprefix[bin])];
     };
-    int node_next = node_at(blockIdx.x * blockDim.x + threadIdx.x);
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
+    int node_next = node_at(first + (int)lane);
+    for (int base = first; base < total; base += stride) {
         int node = node_next;
         node_next = node_at(base + stride + (int)lane);
         bool valid = node >= 0;
@@ -472,8 +486,9 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
     }
     __syncthreads();
     const int total = s_total;
-    if (s_skip || blockIdx.x * blockDim.x >= total) return;
+    if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
     const SceneView& sv = stage_scene(blob);
+    const int first = warp_first_position();
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
@@ -485,8 +500,8 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
         while (g >= s_prefix[bin + 1]) ++bin;
         return ws.order[(size_t)bin * ws.list_cap + (g - s_prefix[bin])];
     };
-    int node_next = node_at(blockIdx.x * blockDim.x + threadIdx.x);
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
+    int node_next = node_at(first + (int)lane);
+    for (int base = first; base < total; base += stride) {
         int node = node_next;
         node_next = node_at(base + stride + (int)lane); // the index of the next iteration travels while this one computes
         bool valid = node >= 0;
@@ -880,37 +895,52 @@ void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkP
     EUCL_DISPATCH_DIM(dim, (k_raygen<3><<<grid, kBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)),
                       (k_raygen<4><<<grid, kBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, hit_ids_out)));
 }
+// fork: the side stream waits for everything enqueued on the main stream so far; join: the main stream waits for the side
+static void fork_side(const Launch& l) {
+    cudaEventRecord(l.ev_fork, l.stream);
+    cudaStreamWaitEvent(l.side, l.ev_fork, 0);
+}
+static void join_side(const Launch& l) {
+    cudaEventRecord(l.ev_join, l.side);
+    cudaStreamWaitEvent(l.stream, l.ev_join, 0);
+}
+
 int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
     // grouped level of a light-capable scene: key 0 -> light build, the other keys -> heavy build;
     // a light-capable scene without cull roots (every ray has key 0) runs the light build in node order
     const bool light_all = l.light_capable && l.n_cull == 0;
     const bool split = l.light_capable && ws.ray_bins != 0;
     const size_t smem_light = l.smem_scene + sizeof(double) * kPlaneChainMax * kLightK2Block;
+    const bool light = light_all || split, heavy = !light_all;
+    const bool fork = light && heavy && l.side != nullptr;
+    cudaStream_t light_stream = fork ? l.side : l.stream;
+    if (fork) fork_side(l);
     int launches = 0;
-    if (light_all || split) {
-        EUCL_DISPATCH_DIM(dim, (k_intersect<3, true><<<l.grid_light_k2, kLightK2Block, smem_light, l.stream>>>(l.blob, ws, level, 1u)),
-                          (k_intersect<4, true><<<l.grid_light_k2, kLightK2Block, smem_light, l.stream>>>(l.blob, ws, level, 1u)));
+    if (light) {
+        EUCL_DISPATCH_DIM(dim, (k_intersect<3, true><<<l.grid_light_k2, kLightK2Block, smem_light, light_stream>>>(l.blob, ws, level, 1u)),
+                          (k_intersect<4, true><<<l.grid_light_k2, kLightK2Block, smem_light, light_stream>>>(l.blob, ws, level, 1u)));
         ++launches;
     }
-    if (!light_all) {
+    if (heavy) {
         const unsigned mask = split ? 0xfffeu : 0xffffu;
         EUCL_DISPATCH_DIM(dim, (k_intersect<3, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level, mask)),
                           (k_intersect<4, false><<<l.grid_max, kBlock, l.smem_bytes, l.stream>>>(l.blob, ws, level, mask)));
         ++launches;
     }
+    if (fork) join_side(l);
     return launches;
 }
 template <int D, bool RAY_BINS, bool GLASS>
-static void launch_shade_one(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
-                             unsigned long long mask, int32_t* hit_ids_out) {
-    if (GLASS) k_shade<D, RAY_BINS, true><<<l.grid_shade, kShadeBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
-    else k_shade<D, RAY_BINS, false><<<l.grid_light, kLightBlock, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
+static void launch_shade_one(const Launch& l, cudaStream_t stream, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                             int level, unsigned long long mask, int32_t* hit_ids_out) {
+    if (GLASS) k_shade<D, RAY_BINS, true><<<l.grid_shade, kShadeBlock, l.smem_scene, stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
+    else k_shade<D, RAY_BINS, false><<<l.grid_light, kLightBlock, l.smem_scene, stream>>>(l.blob, fp, cp, ws, level, mask, hit_ids_out);
 }
 template <int D, bool GLASS>
-static void launch_shade_dim(const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
-                             unsigned long long mask, int32_t* hit_ids_out) {
-    if (ws.ray_bins && level + 1 < fp.max_depth) launch_shade_one<D, true, GLASS>(l, fp, cp, ws, level, mask, hit_ids_out); // the next level will be intersected: group its rays
-    else launch_shade_one<D, false, GLASS>(l, fp, cp, ws, level, mask, hit_ids_out);
+static void launch_shade_dim(const Launch& l, cudaStream_t stream, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                             int level, unsigned long long mask, int32_t* hit_ids_out) {
+    if (ws.ray_bins && level + 1 < fp.max_depth) launch_shade_one<D, true, GLASS>(l, stream, fp, cp, ws, level, mask, hit_ids_out); // the next level will be intersected: group its rays
+    else launch_shade_one<D, false, GLASS>(l, stream, fp, cp, ws, level, mask, hit_ids_out);
 }
 int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
                  int32_t* hit_ids_out) {
@@ -924,16 +954,20 @@ int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkPar
         heavy = ~0ull;
     }
     int launches = 0;
+    const bool fork = light && heavy && l.side != nullptr;
+    cudaStream_t light_stream = fork ? l.side : l.stream;
+    if (fork) fork_side(l);
     if (light) {
-        EUCL_DISPATCH_DIM(dim, (launch_shade_dim<3, false>(l, fp, cp, ws, level, light, hit_ids_out)),
-                          (launch_shade_dim<4, false>(l, fp, cp, ws, level, light, hit_ids_out)));
+        EUCL_DISPATCH_DIM(dim, (launch_shade_dim<3, false>(l, light_stream, fp, cp, ws, level, light, hit_ids_out)),
+                          (launch_shade_dim<4, false>(l, light_stream, fp, cp, ws, level, light, hit_ids_out)));
         ++launches;
     }
     if (heavy) {
-        EUCL_DISPATCH_DIM(dim, (launch_shade_dim<3, true>(l, fp, cp, ws, level, heavy, hit_ids_out)),
-                          (launch_shade_dim<4, true>(l, fp, cp, ws, level, heavy, hit_ids_out)));
+        EUCL_DISPATCH_DIM(dim, (launch_shade_dim<3, true>(l, l.stream, fp, cp, ws, level, heavy, hit_ids_out)),
+                          (launch_shade_dim<4, true>(l, l.stream, fp, cp, ws, level, heavy, hit_ids_out)));
         ++launches;
     }
+    if (fork) join_side(l);
     return launches;
 }
 void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level) {

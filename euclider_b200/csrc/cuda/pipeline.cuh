@@ -113,6 +113,10 @@ struct Launch {
     int grid_light_k2;  // blocks of the light intersect kernel, one wave
     int light_capable;  // SceneHeader::light_capable
     int n_cull;         // SceneHeader::n_cull
+    // The light and the heavy build of a level's kernel do not depend on each other: with a side stream they run
+    // concurrently (fork / join through the two events), so the tail of one overlaps the body of the other.
+    cudaStream_t side;  // nullptr: launch one after the other on `stream`
+    cudaEvent_t ev_fork, ev_join;
 };
 
 #ifndef EUCL_BLOCK

@@ -75,7 +75,7 @@ def stats_to_dict(st: EuclStats) -> dict:
         "level_counts": [int(st.level_counts[i]) for i in range(levels)], "levels": levels,
         "retries": int(st.retries), "launches": int(st.launches), "ray_grouping": int(st.ray_grouping), "ms_total": float(st.ms_total),
         "ms_raygen": float(st.ms_raygen), "ms_intersect": float(st.ms_intersect), "ms_shade": float(st.ms_shade),
-        "ms_resolve": float(st.ms_resolve),
+        "ms_resolve": float(st.ms_resolve), "graph_replays": int(st.graph_replays),
     }
 
 

@@ -279,6 +279,7 @@ typedef struct EuclStats {
     uint32_t ray_grouping; /* 1: this frame walked its rays grouped by reach key (auto-tuned per scene, EUCL_BIN_RAYS forces) */
     float ms_total;     /* device time of the whole call (CUDA events on the render stream) */
     float ms_raygen, ms_intersect, ms_shade, ms_resolve; /* per kernel family */
+    uint32_t graph_replays; /* chunks of this call that ran as one CUDA graph launch (repeated launch parameters) */
 } EuclStats;
 
 int eucl_device_count(void);

@@ -36,7 +36,7 @@ def test_struct_sizes_match_the_header(built_lib):
     assert C.sizeof(_capi.EuclColorOp) == 8 + 12 * 8
     assert C.sizeof(_capi.EuclCamera) == 16 + 4 * 32
     assert C.sizeof(_capi.EuclRenderOpts) == 48
-    assert C.sizeof(_capi.EuclStats) == 24 + 64 * 8 + 16 + 20 + 4  # padded to 8
+    assert C.sizeof(_capi.EuclStats) == 24 + 64 * 8 + 16 + 20 + 4  # five floats + graph_replays
 
 
 def test_no_gpu_means_loud_failure(built_lib):

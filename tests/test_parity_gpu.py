@@ -217,3 +217,28 @@ def test_chunks_shrink_to_the_memory_budget(built_lib, oracle, monkeypatch):
     with pytest.raises(eb.EuclError) as err:
         load("3d_room").render((3840, 90), time=0.25)
     assert err.value.status == -31
+
+
+def test_repeated_frames_replay_as_a_cuda_graph(built_lib, oracle, monkeypatch):
+    """A chunk whose launch parameters repeat is captured once and replayed as one CUDA graph launch
+    (api_device.cu: render_impl); a new pose or time goes back to direct launches.  Same picture either way."""
+    import torch
+
+    env = load("3d_room")
+    w, h = 128, 72
+    ref = oracle.render(env, w, h, time=0.25, variant="det")
+    d = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+    replays = []
+    for _ in range(8):  # the first frames of a scene also settle its arena size and its ray-grouping mode
+        st = env.render_device(d.data_ptr(), (w, h), 0.25)
+        replays.append(st["graph_replays"])
+        assert st["segments"] == ref[2]["segments"] and st["launches"] > 20
+        assert np.array_equal(d.cpu().numpy(), ref[0])
+    assert replays[0] == 0 and replays[-1] == 1 and replays[-2] == 1
+    st = env.render_device(d.data_ptr(), (w, h), 0.75)  # another time: other parameters, direct launches again
+    assert st["graph_replays"] == 0
+    assert np.array_equal(d.cpu().numpy(), oracle.render(env, w, h, time=0.75, variant="det")[0])
+    monkeypatch.setenv("EUCL_GRAPH", "0")
+    for _ in range(3):
+        st = env.render_device(d.data_ptr(), (w, h), 0.75)
+        assert st["graph_replays"] == 0
