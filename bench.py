@@ -47,10 +47,12 @@ DEFAULT_CONFIGS = {
     "4d_cylinders": (3840, 2160), "4d_room": (7680, 4320),
 }
 # BASELINE.json `configs`, in its order: (scene, width, height, max_depth or 0 = the reference's literal 10)
-ALL_CONFIGS = [("3d_fresnel", 1920, 1080, 0), ("3d_room", 3840, 2160, 0), ("3d_hallways", 3840, 2160, 0),
-               ("4d_frame", 3840, 2160, 0), ("4d_cylinders", 3840, 2160, 0), ("4d_room", 7680, 4320, 0),
-               ("4d_room", 7680, 4320, 16)]
-MULTI_GPU_CONFIGS = [("4d_room", 7680, 4320, 0), ("4d_room", 7680, 4320, 16)]
+ALL_CONFIGS = [("3d_fresnel", 1920, 1080, 0, "f64"), ("3d_room", 3840, 2160, 0, "f64"), ("3d_hallways", 3840, 2160, 0, "f64"),
+               ("4d_frame", 3840, 2160, 0, "f64"), ("4d_cylinders", 3840, 2160, 0, "f64"), ("4d_room", 7680, 4320, 0, "f64"),
+               ("4d_room", 7680, 4320, 16, "f64"),
+               # secondary lines: the reference's `low_precision` feature (type F = f32); the headline stays f64
+               ("3d_room", 3840, 2160, 0, "f32"), ("4d_room", 7680, 4320, 0, "f32")]
+MULTI_GPU_CONFIGS = [("4d_room", 7680, 4320, 0, "f64"), ("4d_room", 7680, 4320, 16, "f64")]
 
 
 def scene_flops_per_segment(env) -> int:
@@ -203,7 +205,7 @@ def emit(obj) -> None:
 class Rig:
     """One config (scene, frame size, depth) on this rank: device-resident steps, host-frame steps, teardown."""
 
-    def __init__(self, args, scene, width, height, max_depth, world, rank, local_rank):
+    def __init__(self, args, scene, width, height, max_depth, world, rank, local_rank, precision="f64"):
         import torch
         import torch.distributed as dist
 
@@ -218,6 +220,7 @@ class Rig:
         if max_depth:
             env.camera.max_depth = max_depth
         env.pipeline = eb.EUCL_PIPELINE_MEGAKERNEL if args.pipeline == "megakernel" else eb.EUCL_PIPELINE_WAVEFRONT
+        env.precision = precision
         self.stream = torch.cuda.current_stream()
         env.set_stream(self.stream.cuda_stream, device=local_rank)
         self.env = env
@@ -517,17 +520,20 @@ def main():
         table = []
         todo = ALL_CONFIGS if world == 1 else MULTI_GPU_CONFIGS
         k = max(3, min(args.steps, 6))
-        for scene, w, h, depth in todo:
-            r2 = Rig(args, scene, w, h, depth, world, rank, local_rank)
+        for scene, w, h, depth, precision in todo:
+            r2 = Rig(args, scene, w, h, depth, world, rank, local_rank, precision)
             m2 = measure(r2, k, 3, sample_clocks=False)
             if rank == 0:
                 f2 = scene_flops_per_segment(r2.env)
                 ach = m2["prof_segments"] * f2 / (m2["k_intersect_ms_max"] * 1e-3) / 1e12 if m2["k_intersect_ms_max"] > 0 else None
-                table.append({"scene": scene, "width": w, "height": h, "max_depth": int(r2.env.camera.max_depth), "steps": k,
+                table.append({"scene": scene, "width": w, "height": h, "max_depth": int(r2.env.camera.max_depth), "dtype": precision,
+                              "steps": k,
                               "ms_per_step": m2["ms_per_step"], "fps": 1e3 / m2["ms_per_step"], "mrays_per_s": m2["value"],
                               "segments_per_frame": m2["segments_per_frame"], "e2e_mrays_per_s": m2["e2e"]["value"],
                               "e2e_ms_per_step": m2["e2e"]["ms_per_step"], "flops_per_segment": f2,
-                              "k_intersect_frac": ach / (peak * world) if ach else None, "ray_grouping": m2["ray_grouping"],
+                              # fraction of the f64 issue peak; f32 rows run on the FP32 pipes (twice the lanes): not comparable
+                              "k_intersect_frac": (ach / (peak * world) if ach else None) if precision == "f64" else None,
+                              "ray_grouping": m2["ray_grouping"],
                               "retries": m2["retries"], "rank_device_ms": [min(m2["rank_ms"]), max(m2["rank_ms"])]})
             if world > 1 and args.check:
                 check_results.append(check_gather(r2, args))

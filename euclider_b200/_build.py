@@ -63,13 +63,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if r.returncode != 0:
             raise RuntimeError(f"host compile failed: {src}\n{r.stderr}")
         objs.append(obj)
-    for src in cuda:
-        obj = BUILD / (src.stem + ".cu.o")
-        cmd = [NVCC, *GENCODE, *NVCC_FLAGS, *inc, "-c", str(src), "-o", str(obj)]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed: {src}\n{r.stderr}")
+    # kernels.cu is compiled twice: real = double (namespace eucl) and real = float (namespace eucl_f32, the
+    # reference's `low_precision` feature); api_device.cu dispatches on the scene's precision
+    jobs = [(src, BUILD / (src.stem + ".cu.o"), []) for src in cuda]
+    jobs += [(src, BUILD / (src.stem + "_f32.cu.o"), ["-DEUCL_REAL=float", "-DEUCL_NS=eucl_f32"]) for src in cuda if src.name == "kernels.cu"]
+    procs = [(src, obj, subprocess.Popen([NVCC, *GENCODE, *NVCC_FLAGS, *extra, *inc, "-c", str(src), "-o", str(obj)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)) for src, obj, extra in jobs]
+    for src, obj, proc in procs:
+        _, err = proc.communicate()
+        log.append(err)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {src} -> {obj.name}\n{err}")
         objs.append(obj)
     cmd = [NVCC, *GENCODE, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)

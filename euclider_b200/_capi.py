@@ -104,6 +104,7 @@ class EuclStats(C.Structure):
 EUCL_OK = 0
 EUCL_PIPELINE_WAVEFRONT = 0
 EUCL_PIPELINE_MEGAKERNEL = 1
+EUCL_PRECISION_F64, EUCL_PRECISION_F32 = 0, 1
 PRIM_VOID, PRIM_SPHERE, PRIM_HYPERPLANE, PRIM_HALFSPACE, PRIM_CYLINDER = range(5)
 CSG_LEAF, CSG_UNION, CSG_INTERSECTION, CSG_COMPLEMENT, CSG_SYMDIFF = range(5)
 MAT_VACUUM, MAT_LINEAR_SPACE = range(2)
@@ -131,6 +132,7 @@ PROTOTYPES = {
     "eucl_last_error": (C.c_char_p, []),
     "eucl_version": (C.c_char_p, []),
     "eucl_scene_create": (C.c_int, [C.POINTER(EuclFlatScene), C.c_int, C.POINTER(C.c_void_p)]),
+    "eucl_scene_create_precision": (C.c_int, [C.POINTER(EuclFlatScene), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "eucl_scene_destroy": (None, [C.c_void_p]),
     "eucl_scene_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eucl_band_rows_for_rank": (C.c_uint32, [C.POINTER(EuclRenderOpts)]),

@@ -30,6 +30,9 @@ using namespace eucl;
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                              \
     } while (0)
 
+// the launcher of the scene's precision: namespace eucl holds the f64 build of kernels.cu, eucl_f32 the f32 build
+#define EUCL_PREC(fn) (s->real_bytes == 4 ? eucl_f32::fn : eucl::fn)
+
 int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
     return v && *v ? std::atoi(v) : fallback;
@@ -94,6 +97,7 @@ struct EuclScene {
     uint64_t tune_pixels = 0;    // frame size the two timings belong to
     int warm_frames = 0;         // frames rendered so far
     int n_entities = 0;
+    int real_bytes = 8;        // 8: f64 kernels (the reference's default `type F = f64`); 4: f32 kernels (`low_precision`)
     int arena_capacity = 0;
     double arena_factor = 0.0; // nodes per pixel the arena is sized for (learned from earlier frames)
     cudaGraphExec_t graph_exec = nullptr; // the last repeated chunk as a CUDA graph (render_impl)
@@ -335,7 +339,7 @@ struct MacroBuilder {
     // Conservative bounding spheres (intersect.cuh: Bound) of macro range [first, root]: for each
     // node a sphere containing every point the node's shape can contain and hence every hit its
     // stream can emit (rules in DESIGN.md, "ray/bound culling").  r2 < 0: unbounded.
-    void compute_bounds(int first, int root, std::vector<Bound>* bounds) const {
+    void compute_bounds(int first, int root, double inflate, std::vector<Bound>* bounds) const {
         const int D = f.dim;
         auto none = [] {
             Bound b{};
@@ -460,7 +464,8 @@ struct MacroBuilder {
             if (stored.r2 >= 0) {
                 double cmax = 1.0;
                 for (int k = 0; k < D; ++k) cmax = std::max(cmax, std::fabs(stored.c[k]));
-                const double r = std::sqrt(stored.r2) * (1.0 + 1e-6) + 1e-7 * cmax;
+                // f64 kernels: hit points sit on their surfaces to ~1e-13 relative; f32 kernels: to ~1e-6
+                const double r = std::sqrt(stored.r2) * (1.0 + inflate) + 0.1 * inflate * cmax;
                 stored.r2 = r * r;
                 if (!std::isfinite(stored.r2)) stored.r2 = -1.0;
             }
@@ -604,8 +609,14 @@ void eucl_scene_destroy(EuclScene* s) {
 }
 
 int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
+    return eucl_scene_create_precision(flat, device, EUCL_PRECISION_F64, out);
+}
+
+int eucl_scene_create_precision(const EuclFlatScene* flat, int device, int precision, EuclScene** out) {
     if (!flat || !out) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: null argument");
     *out = nullptr;
+    if (precision != EUCL_PRECISION_F64 && precision != EUCL_PRECISION_F32)
+        return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create_precision: unknown precision");
     if (flat->dim != 3 && flat->dim != 4) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_create: dim must be 3 or 4");
     // the scene is validated before any device is touched (also without one: tests/test_scene_limits.py)
     std::string why;
@@ -621,6 +632,7 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     EUCL_CUDA(cudaSetDevice(device));
     EuclScene* s = new EuclScene();
     s->device = device;
+    s->real_bytes = precision == EUCL_PRECISION_F32 ? 4 : 8;
     s->dim = flat->dim;
     s->n_entities = flat->n_entities;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -725,7 +737,7 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
     }
     std::vector<Bound> bounds(mb.out.size());
     for (int e = 0; e < flat->n_entities; ++e)
-        mb.compute_bounds(dev_entities[(size_t)e].node_first, dev_entities[(size_t)e].node_root, &bounds);
+        mb.compute_bounds(dev_entities[(size_t)e].node_first, dev_entities[(size_t)e].node_root, s->real_bytes == 4 ? 1e-3 : 1e-6, &bounds);
     if (!env_int("EUCL_BOUND_CULL", 1))
         for (auto& b : bounds) b.r2 = -1.0;
     h.n_nodes = (int)mb.out.size();
@@ -808,7 +820,7 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
                                               " B) exceed the shared memory of one CTA (" + std::to_string(smem_optin) + " B)");
     EUCL_CUDA_S(cudaMalloc((void**)&s->d_blob, w.bytes.size()));
     EUCL_CUDA_S(cudaMemcpy(s->d_blob, w.bytes.data(), w.bytes.size(), cudaMemcpyHostToDevice));
-    EUCL_CUDA_S(configure_kernels(s->smem_bytes, s->smem_scene));
+    EUCL_CUDA_S(EUCL_PREC(configure_kernels)(s->smem_bytes, s->smem_scene));
     EUCL_CUDA_S(cudaMallocHost((void**)&s->h_small, sizeof(int32_t) * kSmallInts));
 #undef EUCL_CUDA_S
     *out = s;
@@ -820,46 +832,57 @@ int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out) {
 namespace {
 
 // Camera constants in the reference's order (d3/entity/camera.rs:61-67,174-182; d4: 167-173)
-void frame_params(const EuclCamera& cam, const EuclRenderOpts& o, FrameParams* fp) {
+// T = the scalar the camera arithmetic runs in: double, or float for the reference's `low_precision` feature (the
+// results are stored as doubles either way; the f32 kernels narrow them back without loss)
+template <typename T>
+void frame_params_t(const EuclCamera& cam, const EuclRenderOpts& o, FrameParams* fp) {
     const int D = cam.dim;
     std::memset(fp, 0, sizeof *fp);
-    const double w = (double)o.width, h = (double)o.height;
-    const double pi = 3.14159265358979323846264338327950288;
-    const double fov_rad = pi * (double)cam.fov_deg / 180.0;
-    volatile double diag = std::sqrt(w * w + h * h);
-    volatile double denom = 2.0 * std::tan(fov_rad / 2.0);
-    const double distance = diag / denom;
-    double right[EUCL_MAX_DIM] = {0, 0, 0, 0};
+    const T w = (T)o.width, h = (T)o.height;
+    const T pi = (T)3.14159265358979323846264338327950288;
+    const T fov_rad = pi * (T)cam.fov_deg / (T)180.0;
+    volatile T diag = std::sqrt(w * w + h * h);
+    volatile T denom = (T)2.0 * std::tan(fov_rad / (T)2.0);
+    const T distance = diag / denom;
+    T right[EUCL_MAX_DIM] = {0, 0, 0, 0};
     if (D == 3) {
-        volatile double cx = cam.forward[1] * cam.up[2] - cam.forward[2] * cam.up[1];
-        volatile double cy = cam.forward[2] * cam.up[0] - cam.forward[0] * cam.up[2];
-        volatile double cz = cam.forward[0] * cam.up[1] - cam.forward[1] * cam.up[0];
-        volatile double n2 = cx * cx + cy * cy;
-        n2 = n2 + cz * cz;
-        const double n = std::sqrt(n2);
+        const T f0 = (T)cam.forward[0], f1 = (T)cam.forward[1], f2 = (T)cam.forward[2];
+        const T u0 = (T)cam.up[0], u1 = (T)cam.up[1], u2 = (T)cam.up[2];
+        volatile T p0 = f1 * u2, p1 = f2 * u1, p2 = f2 * u0, p3 = f0 * u2, p4 = f0 * u1, p5 = f1 * u0;
+        volatile T cx = p0 - p1;
+        volatile T cy = p2 - p3;
+        volatile T cz = p4 - p5;
+        volatile T n2 = cx * cx;
+        volatile T t1 = cy * cy, t2 = cz * cz;
+        n2 = n2 + t1;
+        n2 = n2 + t2;
+        const T n = std::sqrt(n2);
         right[0] = cx / n;
         right[1] = cy / n;
         right[2] = cz / n;
     } else {
-        for (int k = 0; k < 4; ++k) right[k] = -cam.left[k];
+        for (int k = 0; k < 4; ++k) right[k] = -(T)cam.left[k];
     }
     for (int k = 0; k < D; ++k) {
-        fp->location[k] = cam.location[k];
-        volatile double step = cam.forward[k] * distance;
-        fp->center[k] = cam.location[k] + step;
-        fp->up[k] = cam.up[k];
+        fp->location[k] = (T)cam.location[k];
+        volatile T step = (T)cam.forward[k] * distance;
+        fp->center[k] = (T)((T)cam.location[k] + step);
+        fp->up[k] = (T)cam.up[k];
         fp->right[k] = right[k];
     }
-    // Duration * 1000 -> whole seconds -> / 1000 (d3/entity/surface.rs:32)
-    fp->time_millis = std::floor(o.time_seconds * 1000.0) / 1000.0;
+    // Duration * 1000 -> whole seconds -> / 1000 (d3/entity/surface.rs:32); `as F` narrows the f64 quotient
+    fp->time_millis = (T)(std::floor(o.time_seconds * 1000.0) / 1000.0);
     fp->width = (int)o.width;
     fp->height = (int)o.height;
     fp->max_depth = (int)cam.max_depth;
 }
+void frame_params(const EuclCamera& cam, const EuclRenderOpts& o, int real_bytes, FrameParams* fp) {
+    if (real_bytes == 4) frame_params_t<float>(cam, o, fp);
+    else frame_params_t<double>(cam, o, fp);
+}
 
-size_t arena_bytes(int dim, size_t cap) {
-    const size_t hit_bytes = (size_t)kHitDoubles * 8;
-    size_t per = (size_t)dim * 16 + 4 + hit_bytes + sizeof(NodeMeta) + 32;
+size_t arena_bytes(int dim, int real_bytes, size_t cap) {
+    size_t per = (size_t)(ray_reals(dim, real_bytes) + kHitReals + 4) * real_bytes + 4 + sizeof(NodeMeta);
     return per * cap + 16 * 16;
 }
 
@@ -873,9 +896,10 @@ Workspace carve(EuclScene* s, int dim, int cap, int list_cap) {
         p += align16(bytes);
         return r;
     };
-    ws.ray = (double*)take((size_t)dim * 16 * cap);
-    ws.hit = (double*)take((size_t)kHitDoubles * 8 * (size_t)cap);
-    ws.res = (double*)take((size_t)32 * cap);
+    const size_t rb = (size_t)s->real_bytes;
+    ws.ray = take((size_t)ray_reals(dim, s->real_bytes) * rb * cap);
+    ws.hit = take((size_t)kHitReals * rb * cap);
+    ws.res = take((size_t)4 * rb * cap);
     ws.meta = (NodeMeta*)take(sizeof(NodeMeta) * (size_t)cap);
     ws.ray_cur = (int32_t*)take((size_t)4 * cap);
     int32_t* small = (int32_t*)s->small.ptr;
@@ -899,7 +923,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                 EuclStats* stats) {
     const int dim = s->dim;
     FrameParams fp;
-    frame_params(*cam, *o, &fp);
+    frame_params(*cam, *o, s->real_bytes, &fp);
     const int width = (int)o->width;
     const uint32_t my_rows = eucl_band_rows_for_rank(o);
     EuclStats st{};
@@ -938,7 +962,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
         const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && kBinsPerEntity * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
         const size_t n_lists = (want_rorder ? (size_t)kRayBins : 0) + (want_order ? (size_t)(kBinsPerEntity * s->n_entities + 1) : 0);
-        auto workspace_bytes = [&](size_t cap, size_t list_cap) { return arena_bytes(dim, cap) + sizeof(int32_t) * n_lists * list_cap; };
+        auto workspace_bytes = [&](size_t cap, size_t list_cap) { return arena_bytes(dim, s->real_bytes, cap) + sizeof(int32_t) * n_lists * list_cap; };
 
         for (int row0 = 0; row0 < (int)my_rows;) {
             ChunkParams cp{};
@@ -967,7 +991,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     if (cap_mb > 0) budget = std::min(budget, (size_t)cap_mb << 20);
                     too_big = workspace_bytes((size_t)want, (size_t)want_list) > budget;
                     if (!too_big) {
-                        cudaError_t e = s->nodes.ensure(arena_bytes(dim, (size_t)want));
+                        cudaError_t e = s->nodes.ensure(arena_bytes(dim, s->real_bytes, (size_t)want));
                         if (e == cudaSuccess && want_rorder) e = s->rorder.ensure(sizeof(int32_t) * (size_t)kRayBins * (size_t)want_list);
                         if (e == cudaSuccess && want_order) e = s->order.ensure(sizeof(int32_t) * (size_t)(kBinsPerEntity * s->n_entities + 1) * (size_t)want_list);
                         if (e == cudaSuccess) {
@@ -1029,34 +1053,34 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     }
                     mark(-1);
                     if (o->pipeline == EUCL_PIPELINE_MEGAKERNEL) {
-                        launch_camera_entity(dim, l, fp, ws);
+                        EUCL_PREC(launch_camera_entity)(dim, l, fp, ws);
                         dbg("k_camera_entity", 0);
-                        launch_megakernel(dim, l, fp, cp, ws, d_rgb, d_hit);
+                        EUCL_PREC(launch_megakernel)(dim, l, fp, cp, ws, d_rgb, d_hit);
                         mark(1);
                         launches += 2;
                     } else {
-                        launch_raygen(dim, l, fp, cp, ws, d_hit);
+                        EUCL_PREC(launch_raygen)(dim, l, fp, cp, ws, d_hit);
                         dbg("k_raygen", 0);
                         mark(0);
                         for (int level = 0; level < (int)cam->max_depth; ++level) {
-                            launches += launch_intersect(dim, l, ws, level);
+                            launches += EUCL_PREC(launch_intersect)(dim, l, ws, level);
                             dbg("k_intersect", level);
                             mark(1);
-                            launches += launch_shade(dim, l, fp, cp, ws, level, d_hit);
+                            launches += EUCL_PREC(launch_shade)(dim, l, fp, cp, ws, level, d_hit);
                             dbg("k_shade", level);
                             mark(2);
                         }
-                        launches += launch_shade(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
+                        // the nodes of the last level are background lookups (depth 0: mod.rs:157,183).  Measured and not kept:
+                        // finishing them inside k_shade of the level above, from the child direction in registers (one launch
+                        // and one ray record per node less, but the lookups then run at the heavy kernel's occupancy:
+                        // 3d_room shade 7.14 + 0.47 -> 7.34 + 0.67 ms)
+                        launches += EUCL_PREC(launch_shade)(dim, l, fp, cp, ws, (int)cam->max_depth, d_hit);
                         dbg("k_shade", (int)cam->max_depth);
                         mark(2);
-                        for (int level = (int)cam->max_depth - 1; level >= 1; --level) {
-                            launch_resolve(dim, l, ws, level);
-                            dbg("k_resolve", level);
-                        }
-                        launch_final(dim, l, fp, cp, ws, d_rgb);
-                        dbg("k_final", 0);
+                        launches += EUCL_PREC(launch_resolve_and_final)(dim, l, fp, cp, ws, d_rgb);
+                        dbg("k_resolve / k_final", 0);
                         mark(3);
-                        launches += 2 + (cam->max_depth == 0 ? 0 : cam->max_depth - 1); // raygen, final, resolve levels
+                        launches += 1; // raygen
                     }
                     cudaMemcpyAsync(s->h_small, s->small.ptr, sizeof(int32_t) * kSmallInts, cudaMemcpyDeviceToHost, s->stream);
                     return launches;
@@ -1297,7 +1321,7 @@ int eucl_trace_path(EuclScene* s, const double* location, const double* directio
     }
     EUCL_CUDA(cudaMemcpyAsync(d_in, h_in, sizeof h_in, cudaMemcpyHostToDevice, s->stream));
     Launch l{s->stream, s->d_blob, s->smem_bytes, s->smem_scene, 1, 1, 1, 1, 1ull, 0ull, 1, 0, 0, nullptr, nullptr, nullptr};
-    launch_trace_path(D, l, d_in, distance, d_out, d_found);
+    EUCL_PREC(launch_trace_path)(D, l, d_in, distance, d_out, d_found);
     double h_out[2 * EUCL_MAX_DIM];
     int h_found = 0;
     EUCL_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, s->stream));

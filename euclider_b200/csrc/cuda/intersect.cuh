@@ -11,35 +11,36 @@
 #include "scene_dev.cuh"
 #include "vecmath.cuh"
 
-namespace eucl {
+namespace EUCL_NS {
+using namespace eucl;
 
 constexpr int CSG_ARENA = 256;     // compact hits per thread (scene_create validates programs against it)
 constexpr int CSG_LIST_STACK = 16; // nesting depth of pending child lists
 constexpr int CHAIN_ROOT_CAP = 32; // hits of a chain that is an entity's whole shape (<= 16 leaves)
 
 struct CHit {
-    double t;
+    real t;
     int prim;
     int flags; // bit 0: second root of the primitive; bit 1: normal negated (Complement / SymDiff)
 };
 
 // Roots of a*t^2 + b*t + c with the reference's selection of non-negative roots
 // (shape.rs:672-694 sphere, :969-991 cylinder).  Returns the number of hits.
-__device__ __forceinline__ int quadratic_hits(double a, double b, double c, double& t_first, double& t_second) {
-    double disc = b * b - 4.0 * a * c;
-    if (disc < 0.0) return 0;
-    double d_sqrt = sqrt(disc);
-    double t1 = (-b - d_sqrt) / (2.0 * a);
-    double t2 = (-b + d_sqrt) / (2.0 * a);
-    if (t1 >= 0.0) {
+__device__ __forceinline__ int quadratic_hits(real a, real b, real c, real& t_first, real& t_second) {
+    real disc = b * b - R(4.0) * a * c;
+    if (disc < R(0.0)) return 0;
+    real d_sqrt = sqrt(disc);
+    real t1 = (-b - d_sqrt) / (R(2.0) * a);
+    real t2 = (-b + d_sqrt) / (R(2.0) * a);
+    if (t1 >= R(0.0)) {
         t_first = t1;
-        if (t2 >= 0.0) {
+        if (t2 >= R(0.0)) {
             t_second = t2;
             return 2;
         }
         return 1;
     }
-    if (t2 >= 0.0) {
+    if (t2 >= R(0.0)) {
         t_first = t2;
         return 1;
     }
@@ -48,37 +49,37 @@ __device__ __forceinline__ int quadratic_hits(double a, double b, double c, doub
 
 // Parametric distances at which the ray meets primitive `prim` (sorted, t >= 0 only).
 template <int D>
-__device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const Vec<D>& o, const Vec<D>& d, double& t0,
-                                          double& t1) {
+__device__ __forceinline__ int prim_roots(const SceneView& sv, int prim, const Vec<D>& o, const Vec<D>& d, real& t0,
+                                          real& t1) {
     const int n = sv.n_prims;
     const int kind = sv.prim_kind()[prim];
     const double* __restrict__ rec = sv.planes() + (size_t)prim * kPlaneStride; // AoS: [v0[0..3], s0, s1]
     if (kind == EUCL_PRIM_SPHERE) { // shape.rs:662-670
         Vec<D> center = load_vec<D>(rec, 1);
-        double radius = rec[4];
+        real radius = R(rec[4]);
         Vec<D> rel = o - center;
-        double a = norm_squared(d);
-        double b = 2.0 * dot(d, rel);
-        double c = norm_squared(rel) - radius * radius;
+        real a = norm_squared(d);
+        real b = R(2.0) * dot(d, rel);
+        real c = norm_squared(rel) - radius * radius;
         return quadratic_hits(a, b, c, t0, t1);
     }
     if (kind == EUCL_PRIM_HYPERPLANE || kind == EUCL_PRIM_HALFSPACE) { // shape.rs:788-793
         Vec<D> nrm = load_vec<D>(rec, 1);
-        double t = -(dot(nrm, o) + rec[4]) / dot(nrm, d);
-        if (t < 0.0) return 0; // NaN and +inf pass, exactly like the reference
+        real t = -(dot(nrm, o) + R(rec[4])) / dot(nrm, d);
+        if (t < R(0.0)) return 0; // NaN and +inf pass, exactly like the reference
         t0 = t;
         return 1;
     }
     if (kind == EUCL_PRIM_CYLINDER) { // shape.rs:946-953
         Vec<D> center = load_vec<D>(rec, 1);
         Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
-        double radius = rec[4];
+        real radius = R(rec[4]);
         Vec<D> a_vec = d - axis * dot(d, axis);
         Vec<D> delta = o - center;
         Vec<D> c_vec = delta - axis * dot(delta, axis);
-        double a = norm_squared(a_vec);
-        double b = (1.0 + 1.0) * dot(a_vec, c_vec);
-        double c = norm_squared(c_vec) - radius * radius;
+        real a = norm_squared(a_vec);
+        real b = (R(1.0) + R(1.0)) * dot(a_vec, c_vec);
+        real c = norm_squared(c_vec) - radius * radius;
         return quadratic_hits(a, b, c, t0, t1);
     }
     return 0; // VoidShape: shape.rs:622-631
@@ -91,17 +92,17 @@ __device__ __forceinline__ bool prim_inside(const SceneView& sv, int prim, const
     const int kind = sv.prim_kind()[prim];
     const double* __restrict__ rec = sv.planes() + (size_t)prim * kPlaneStride;
     if (kind == EUCL_PRIM_HALFSPACE) {
-        double r = dot(load_vec<D>(rec, 1), p) + rec[4];
-        return rec[5] == rust_signum(r);
+        real r = dot(load_vec<D>(rec, 1), p) + R(rec[4]);
+        return R(rec[5]) == rust_signum(r);
     }
     if (kind == EUCL_PRIM_SPHERE) {
-        double radius = rec[4];
+        real radius = R(rec[4]);
         return norm_squared(load_vec<D>(rec, 1) - p) <= radius * radius;
     }
     if (kind == EUCL_PRIM_CYLINDER) {
         Vec<D> center = load_vec<D>(rec, 1);
         Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
-        double radius = rec[4];
+        real radius = R(rec[4]);
         Vec<D> on_axis = axis * dot(axis, p - center) + center;
         return norm_squared(p - on_axis) <= radius * radius;
     }
@@ -179,11 +180,11 @@ __device__ __noinline__ int material_at(const SceneView& sv, EUCL_VARG(Vec<D>) p
         const int root = sv.entities()[e].node_root;
         // a point outside the (inflated) bounding sphere of the shape cannot be inside it; NaN -> not skipped
         const Bound& bnd = sv.bounds()[root];
-        if (bnd.r2 >= 0.0) {
-            double dist2 = 0.0;
+        if (R(bnd.r2) >= R(0.0)) {
+            real dist2 = R(0.0);
 #pragma unroll
-            for (int k = 0; k < D; ++k) dist2 += (p[k] - bnd.c[k]) * (p[k] - bnd.c[k]);
-            if (dist2 > bnd.r2) continue;
+            for (int k = 0; k < D; ++k) dist2 += (p[k] - R(bnd.c[k])) * (p[k] - R(bnd.c[k]));
+            if (dist2 > R(bnd.r2)) continue;
         }
         if (node_inside<D>(sv, root, p)) return e;
     }
@@ -197,14 +198,14 @@ __device__ __noinline__ int material_at(const SceneView& sv, EUCL_VARG(Vec<D>) p
 // the node's hit list is empty and the whole evaluation is skipped.  NaN anywhere makes every
 // comparison false: such rays are never culled and take the exact path.
 template <int D>
-__device__ __forceinline__ bool ray_misses(const Bound& bnd, const Vec<D>& o, const Vec<D>& d, double dd) {
-    if (!(bnd.r2 >= 0.0)) return false;
+__device__ __forceinline__ bool ray_misses(const Bound& bnd, const Vec<D>& o, const Vec<D>& d, real dd) {
+    if (!(R(bnd.r2) >= R(0.0))) return false;
     Vec<D> rel;
 #pragma unroll
-    for (int k = 0; k < D; ++k) rel[k] = o[k] - bnd.c[k];
-    const double b = dot(d, rel);
-    const double c = dot(rel, rel) - bnd.r2;
-    return (b * b - dd * c < 0.0) || (c > 0.0 && b > 0.0);
+    for (int k = 0; k < D; ++k) rel[k] = o[k] - R(bnd.c[k]);
+    const real b = dot(d, rel);
+    const real c = dot(rel, rel) - R(bnd.r2);
+    return (b * b - dd * c < R(0.0)) || (c > R(0.0) && b > R(0.0));
 }
 
 // Reach key of a ray: which of the scene's bounded, non-trivial entities its half-line can reach.
@@ -212,7 +213,7 @@ __device__ __forceinline__ bool ray_misses(const Bound& bnd, const Vec<D>& o, co
 // grouped by this key (kernels.cu).  Purely an ordering hint: results do not depend on it.
 template <int D>
 __device__ __forceinline__ int reach_key(const SceneView& sv, const Vec<D>& o, const Vec<D>& d) {
-    const double dd = dot(d, d);
+    const real dd = dot(d, d);
     int key = 0;
     for (int k = 0; k < sv.n_cull; ++k)
         if (!ray_misses<D>(sv.bounds()[sv.cull_root[k]], o, d, dd)) key |= 1 << k;
@@ -228,7 +229,7 @@ __device__ __forceinline__ int reach_key(const SceneView& sv, const Vec<D>& o, c
 template <int D>
 __device__ __forceinline__ int chain_eval(const SceneView& sv, int op, int p0, int count, const Vec<D>& o, const Vec<D>& d,
                                           CHit* L, CHit* T, int cap, bool first_only) {
-    double t0 = 0.0, t1 = 0.0;
+    real t0 = R(0.0), t1 = R(0.0);
     int n = prim_roots<D>(sv, p0, o, d, t0, t1);
     if (n > 0) L[0] = CHit{t0, p0, 0};
     if (n > 1) L[1] = CHit{t1, p0, 1};
@@ -240,7 +241,7 @@ __device__ __forceinline__ int chain_eval(const SceneView& sv, int op, int p0, i
         while (m < limit) {
             const bool has_a = ia < n, has_b = ib < nb;
             if (!has_a && !has_b) break;
-            const double tb = ib == 0 ? t0 : t1;
+            const real tb = ib == 0 ? t0 : t1;
             CHit h;
             bool in;
             if (has_a && (!has_b || L[ia].t < tb)) {
@@ -263,7 +264,7 @@ __device__ __forceinline__ int chain_eval(const SceneView& sv, int op, int p0, i
 // Membership rows of G consecutive hit points of a plane chain against all N planes.
 template <int D, int G>
 __device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N, const Vec<D>& o, const Vec<D>& d,
-                                           const double* ts, int ts_stride, int i0, unsigned long long& inside) {
+                                           const real* ts, int ts_stride, int i0, unsigned long long& inside) {
     Vec<D> p[G];
     unsigned rows[G];
 #pragma unroll
@@ -277,12 +278,12 @@ __device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N
         const double* r = rec + j * kPlaneStride;
         Vec<D> nrm;
 #pragma unroll
-        for (int k = 0; k < D; ++k) nrm[k] = r[k];
-        const double c = r[4];
-        const bool s_neg = r[5] < 0.0;
+        for (int k = 0; k < D; ++k) nrm[k] = R(r[k]);
+        const real c = R(r[4]);
+        const bool s_neg = r[5] < R(0.0);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const double v = dot(nrm, p[g]) + c;
+            const real v = dot(nrm, p[g]) + c;
             const bool in = !isnan(v) && ((__double2hiint(v) < 0) == s_neg);
             rows[g] |= (in ? 1u : 0u) << j;
         }
@@ -308,7 +309,7 @@ __device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N
 constexpr int kPlaneChainMax = 8;
 template <int D>
 __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, int N, const Vec<D>& o, const Vec<D>& d,
-                                           bool first_only, double* ts, int ts_stride, unsigned long long& list_out) {
+                                           bool first_only, real* ts, int ts_stride, unsigned long long& list_out) {
     const double* __restrict__ rec = sv.planes() + (size_t)p0 * kPlaneStride;
     unsigned exists = 0u;
 #pragma unroll 1
@@ -316,10 +317,10 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         const double* r = rec + i * kPlaneStride;
         Vec<D> nrm;
 #pragma unroll
-        for (int k = 0; k < D; ++k) nrm[k] = r[k];
-        const double t = -(dot(nrm, o) + r[4]) / dot(nrm, d);
+        for (int k = 0; k < D; ++k) nrm[k] = R(r[k]);
+        const real t = -(dot(nrm, o) + R(r[4])) / dot(nrm, d);
         ts[i * ts_stride] = t;
-        if (!(t < 0.0)) exists |= 1u << i; // NaN and +inf pass
+        if (!(t < R(0.0))) exists |= 1u << i; // NaN and +inf pass
     }
     const bool want_in = op == EUCL_CSG_INTERSECTION;
     if (first_only) {
@@ -332,12 +333,12 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         // is one of the N - 1 evaluated here, so m is emitted first every time.  (Rays inside a room or a box: always.)
         // Anything else -- ties, NaN, a rejected m -- takes the general evaluation below.
         int m = -1;
-        double tm = 0.0;
+        real tm = R(0.0);
         bool clean = true;
 #pragma unroll 1
         for (int i = 0; i < N; ++i) {
             if (!((exists >> i) & 1u)) continue;
-            const double t = ts[i * ts_stride];
+            const real t = ts[i * ts_stride];
             if (isnan(t)) clean = false;
             if (m < 0 || t < tm) {
                 m = i;
@@ -356,9 +357,9 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
                 const double* r = rec + j * kPlaneStride;
                 Vec<D> nrm;
 #pragma unroll
-                for (int k = 0; k < D; ++k) nrm[k] = r[k];
-                const double v = dot(nrm, pm) + r[4];
-                const bool in = !isnan(v) && ((__double2hiint(v) < 0) == (r[5] < 0.0));
+                for (int k = 0; k < D; ++k) nrm[k] = R(r[k]);
+                const real v = dot(nrm, pm) + R(r[4]);
+                const bool in = !isnan(v) && ((__double2hiint(v) < 0) == (r[5] < R(0.0)));
                 const bool tie = j != m && ((exists >> j) & 1u) && !(tm < ts[j * ts_stride]);
                 if (j != m && (in != want_in || tie)) ok = false;
             }
@@ -403,7 +404,7 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         const unsigned mask_k = (unsigned)(inside >> (k * N)) & prefix;
         const bool b_in = want_in ? mask_k == prefix : mask_k != 0u; // inside the fold of leaves 0..k-1
         bool b_pending = (exists >> k) & 1u;
-        const double tk = ts[k * ts_stride];
+        const real tk = ts[k * ts_stride];
         const int limit = (first_only && k == N - 1) ? 1 : N;
         unsigned long long T = 0ull;
         int ia = 0, m = 0;
@@ -441,16 +442,16 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
 // (ComposableShape::intersect_linear + the four merge iterators, shape.rs:204-584).
 template <int D>
 __device__ __forceinline__ bool csg_first(const SceneView& sv, int first, int root, const Vec<D>& o, const Vec<D>& d,
-                                          double* ts, int ts_stride, CHit& out) {
+                                          real* ts, int ts_stride, CHit& out) {
     const MNode* mn = reinterpret_cast<const MNode*>(sv.nodes());
-    const double dd = dot(d, d);
+    const real dd = dot(d, d);
     CHit arena[CSG_ARENA];
     int lstart[CSG_LIST_STACK], llen[CSG_LIST_STACK];
     int sp = 0, top = 0;
     for (int n = first; n <= root; ++n) {
         const MNode nd = mn[n];
         if (nd.kind == M_PRIM) {
-            double t0 = 0.0, t1 = 0.0;
+            real t0 = R(0.0), t1 = R(0.0);
             const int c = prim_roots<D>(sv, nd.a, o, d, t0, t1);
             lstart[sp] = top;
             llen[sp] = c;
@@ -575,17 +576,17 @@ struct ClosestHit {
     int entity; // -1: no hit
     int prim;
     int flags;
-    double t;
+    real t;
 };
 
 // trace_closest, distance part: every surfaced entity (including the one the ray is inside) is
 // asked for the FIRST item of its stream; a candidate replaces the current one only if it is
 // strictly closer (mod.rs:127-128), so a NaN distance wins only as the very first candidate.
 template <int D>
-__device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, double* ts,
+__device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, real* ts,
                                                   int ts_stride) {
-    ClosestHit best{-1, 0, 0, 0.0};
-    const double dd = dot(d, d);
+    ClosestHit best{-1, 0, 0, R(0.0)};
+    const real dd = dot(d, d);
     for (int e = 0; e < sv.n_entities; ++e) {
         const EuclEntity ent = sv.entities()[e];
         if (ent.surface < 0) continue;
@@ -594,7 +595,7 @@ __device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec
         const MNode root = reinterpret_cast<const MNode*>(sv.nodes())[ent.node_root];
         if (root.kind != M_PRIM && ray_misses<D>(sv.bounds()[ent.node_root], o, d, dd)) continue; // no hit can come from this entity
         if (root.kind == M_PRIM) {
-            double t0 = 0.0, t1 = 0.0;
+            real t0 = R(0.0), t1 = R(0.0);
             found = prim_roots<D>(sv, root.a, o, d, t0, t1) > 0;
             h = CHit{t0, root.a, 0};
         } else { // one call site: the evaluator (and the chain code inside it) exists once in the kernel
@@ -610,14 +611,14 @@ __device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec
 // outside the bound of every cull root, so those yield no hit (same argument as ray_misses) and are skipped
 // without a test.  No general CSG evaluator, no hit arena: the kernel built on this keeps more warps resident.
 template <int D>
-__device__ __forceinline__ ClosestHit closest_hit_light(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, double* ts,
+__device__ __forceinline__ ClosestHit closest_hit_light(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, real* ts,
                                                         int ts_stride) {
-    ClosestHit best{-1, 0, 0, 0.0};
+    ClosestHit best{-1, 0, 0, R(0.0)};
     for (int e = 0; e < sv.n_entities; ++e) {
         const int flags = sv.ent_flags()[e];
         if (!(flags & ENT_SURFACED) || (flags & ENT_CULL_ROOT)) continue;
         const MNode root = reinterpret_cast<const MNode*>(sv.nodes())[sv.entities()[e].node_root];
-        double t0 = 0.0, t1 = 0.0;
+        real t0 = R(0.0), t1 = R(0.0);
         int prim = root.a;
         bool found;
         if (flags & ENT_PRIM) {
@@ -638,7 +639,7 @@ __device__ __forceinline__ ClosestHit closest_hit_light(const SceneView& sv, con
 // (shape.rs:700-728 sphere, :795-806 plane, :858-861 half-space, :993-1024 cylinder).
 template <int D>
 __device__ __forceinline__ void hit_geometry(const SceneView& sv, int prim, int flags, const Vec<D>& o, const Vec<D>& d,
-                                             double t, Vec<D>& p, Vec<D>& nrm) {
+                                             real t, Vec<D>& p, Vec<D>& nrm) {
     const int n = sv.n_prims;
     const int kind = sv.prim_kind()[prim];
     if (kind == EUCL_PRIM_SPHERE) {
@@ -647,9 +648,9 @@ __device__ __forceinline__ void hit_geometry(const SceneView& sv, int prim, int 
     } else if (kind == EUCL_PRIM_CYLINDER) {
         Vec<D> center = load_vec<D>(sv.prim_v0() + prim, n);
         Vec<D> axis = load_vec<D>(sv.prim_v1() + prim, n);
-        double t_first = t;
+        real t_first = t;
         if (flags & 1) { // the second hit reuses the axis point of the FIRST hit (shape.rs:999,1017)
-            double r0 = 0.0, r1 = 0.0;
+            real r0 = R(0.0), r1 = R(0.0);
             prim_roots<D>(sv, prim, o, d, r0, r1);
             t_first = r0;
         }
@@ -660,9 +661,9 @@ __device__ __forceinline__ void hit_geometry(const SceneView& sv, int prim, int 
     } else {
         p = d * t + o;
         nrm = load_vec<D>(sv.prim_v0() + prim, n);
-        if (kind == EUCL_PRIM_HALFSPACE) nrm = nrm * -sv.prim_s1()[prim];
+        if (kind == EUCL_PRIM_HALFSPACE) nrm = nrm * -R(sv.prim_s1()[prim]);
     }
     if (flags & 2) nrm = -nrm;
 }
 
-} // namespace eucl
+} // namespace EUCL_NS

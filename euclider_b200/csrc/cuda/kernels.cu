@@ -9,9 +9,11 @@
 // (src/universe/entity/surface.rs:62-162).  Compiled with -fmad=false.
 #include "pipeline.cuh"
 #include "shade.cuh"
+#include <cstdio>
 #include <cstdlib>
 
-namespace eucl {
+namespace EUCL_NS {
+using namespace eucl;
 
 namespace {
 
@@ -24,73 +26,97 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // node arena access (array-of-structures records made of 128-bit words)
 
+// One 128-bit word of `real`s: two doubles or four floats.  Every record of the arena is a whole number of them.
+constexpr int kWordReals = 16 / (int)sizeof(real);
+struct __align__(16) Word {
+    real v[kWordReals];
+};
+template <int N> // N reals, N % kWordReals == 0
+__device__ __forceinline__ void store_words(void* base, size_t record, const real (&v)[N]) {
+    Word* rec = reinterpret_cast<Word*>(base) + record * (N / kWordReals);
+#pragma unroll
+    for (int k = 0; k < N / kWordReals; ++k) {
+        Word w;
+#pragma unroll
+        for (int j = 0; j < kWordReals; ++j) w.v[j] = v[k * kWordReals + j];
+        rec[k] = w;
+    }
+}
+template <int N, int NLOAD = N> // reads the first NLOAD reals (rounded up to whole words) of a record of N
+__device__ __forceinline__ void load_words(const void* base, size_t record, real (&v)[N]) {
+    const Word* rec = reinterpret_cast<const Word*>(base) + record * (N / kWordReals);
+#pragma unroll
+    for (int k = 0; k < (NLOAD + kWordReals - 1) / kWordReals; ++k) {
+        const Word w = rec[k];
+#pragma unroll
+        for (int j = 0; j < kWordReals; ++j) v[k * kWordReals + j] = w.v[j];
+    }
+}
+
 template <int D>
 __device__ __forceinline__ void store_ray(const Workspace& ws, int node, const Vec<D>& o, const Vec<D>& d, int cur) {
-    double2* rec = reinterpret_cast<double2*>(ws.ray + (size_t)node * (2 * D));
-    double v[2 * D];
+    constexpr int K = ray_reals(D, (int)sizeof(real));
+    real v[K];
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        v[k] = o[k];
-        v[D + k] = d[k];
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) rec[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    for (int k = 0; k < K; ++k) v[k] = k < D ? o[k < D ? k : 0] : (k < 2 * D ? d[k < 2 * D ? k - D : 0] : R(0.0));
+    store_words<K>(ws.ray, (size_t)node, v);
     ws.ray_cur[node] = cur;
 }
 template <int D>
 __device__ __forceinline__ void load_ray(const Workspace& ws, int node, Vec<D>& o, Vec<D>& d) {
-    const double2* rec = reinterpret_cast<const double2*>(ws.ray + (size_t)node * (2 * D));
-    double v[2 * D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        double2 t = rec[k];
-        v[2 * k] = t.x;
-        v[2 * k + 1] = t.y;
-    }
+    constexpr int K = ray_reals(D, (int)sizeof(real));
+    real v[K];
+    load_words<K, 2 * D>(ws.ray, (size_t)node, v);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         o[k] = v[k];
         d[k] = v[D + k];
     }
 }
+// (entity, exiting) in one 32-bit pattern: entity + 1 in the low 31 bits (entity >= -1), exiting in the top bit
+struct HitHead {
+    real t, cos_raw, angle_raw;
+    int32_t entity, exiting;
+};
+__device__ __forceinline__ real pack_hit_ids(int entity, int exiting) {
+    const unsigned bits = (unsigned)(entity + 1) | (exiting ? 0x80000000u : 0u);
+    if (kRealIsDouble) return (real)__hiloint2double(0, (int)bits);
+    return (real)__int_as_float((int)bits);
+}
+__device__ __forceinline__ unsigned unpack_hit_ids(real v) {
+    if (kRealIsDouble) return (unsigned)__double2loint((double)v);
+    return (unsigned)__float_as_int((float)v);
+}
 template <int D>
 __device__ __forceinline__ void store_hit(const Workspace& ws, int node, const HitHead& h, const Vec<D>& n) {
-    constexpr int K = kHitDoubles;
-    double v[K];
+    constexpr int K = kHitReals;
+    real v[K];
     v[0] = h.t;
     v[1] = h.cos_raw;
-    v[2] = __hiloint2double(h.exiting, h.entity); // low word = entity, high word = exiting
+    v[2] = pack_hit_ids(h.entity, h.exiting);
     v[3] = h.angle_raw;
 #pragma unroll
-    for (int k = 4; k < K; ++k) v[k] = k - 4 < D ? n[k - 4 < D ? k - 4 : 0] : 0.0;
-    double2* rec = reinterpret_cast<double2*>(ws.hit + (size_t)node * K);
-#pragma unroll
-    for (int k = 0; k < K / 2; ++k) rec[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    for (int k = 4; k < K; ++k) v[k] = k - 4 < D ? n[k - 4 < D ? k - 4 : 0] : R(0.0);
+    store_words<K>(ws.hit, (size_t)node, v);
 }
 template <int D>
 __device__ __forceinline__ HitHead load_hit(const Workspace& ws, int node, Vec<D>& n) {
-    constexpr int K = kHitDoubles;
-    const double2* rec = reinterpret_cast<const double2*>(ws.hit + (size_t)node * K);
-    double v[K];
-#pragma unroll
-    for (int k = 0; k < (4 + D + 1) / 2; ++k) {
-        const double2 w = rec[k];
-        v[2 * k] = w.x;
-        v[2 * k + 1] = w.y;
-    }
+    constexpr int K = kHitReals;
+    real v[K];
+    load_words<K, 4 + D>(ws.hit, (size_t)node, v);
 #pragma unroll
     for (int k = 0; k < D; ++k) n[k] = v[4 + k];
-    return HitHead{v[0], v[1], v[3], __double2loint(v[2]), __double2hiint(v[2])};
+    const unsigned ids = unpack_hit_ids(v[2]);
+    return HitHead{v[0], v[1], v[3], (int)(ids & 0x7fffffffu) - 1, (int)(ids >> 31)};
 }
 __device__ __forceinline__ void store_res(const Workspace& ws, int node, const Rgba& c) {
-    double2* rec = reinterpret_cast<double2*>(ws.res + (size_t)node * 4);
-    rec[0] = make_double2(c.r, c.g);
-    rec[1] = make_double2(c.b, c.a);
+    const real v[4] = {c.r, c.g, c.b, c.a};
+    store_words<4>(ws.res, (size_t)node, v);
 }
 __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
-    const double2* rec = reinterpret_cast<const double2*>(ws.res + (size_t)node * 4);
-    const double2 rg = rec[0], ba = rec[1];
-    return Rgba{rg.x, rg.y, ba.x, ba.y};
+    real v[4];
+    load_words<4>(ws.res, (size_t)node, v);
+    return Rgba{v[0], v[1], v[2], v[3]};
 }
 
 // First queue position of this warp in the grid-stride walk of the queue kernels (CTA-contiguous).  Measured and not kept:
@@ -100,9 +126,9 @@ __device__ __forceinline__ int warp_first_position() { return (int)(blockIdx.x *
 
 // Per-thread scratch column for plane_chain (kPlaneChainMax doubles per thread, element i of thread
 // t at [i * blockDim.x + t]): lives in dynamic shared memory right after the staged scene.
-__device__ __forceinline__ double* plane_scratch(const uint8_t* __restrict__ blob) {
+__device__ __forceinline__ real* plane_scratch(const uint8_t* __restrict__ blob) {
     const int blob_bytes = reinterpret_cast<const SceneHeader*>(blob)->blob_bytes;
-    return reinterpret_cast<double*>(g_smem + scene_smem_bytes(blob_bytes)) + threadIdx.x;
+    return reinterpret_cast<real*>(g_smem + scene_smem_bytes(blob_bytes)) + threadIdx.x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -112,7 +138,7 @@ __device__ __forceinline__ double* plane_scratch(const uint8_t* __restrict__ blo
 // and its orientation relative to the ray (mod.rs:114-125).
 template <int D>
 __device__ __forceinline__ int intersect_ray(const SceneView& sv, const Vec<D>& o, const Vec<D>& d, bool& exiting, Vec<D>& p,
-                                             Vec<D>& n_raw, double& cos_raw, double& angle_raw, double* ts, int ts_stride) {
+                                             Vec<D>& n_raw, real& cos_raw, real& angle_raw, real* ts, int ts_stride) {
     const ClosestHit h = closest_hit<D>(sv, o, d, ts, ts_stride);
     if (h.entity < 0) return -1;
     hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n_raw);
@@ -129,7 +155,7 @@ struct ChildRay {
 };
 template <int D>
 struct ShadeOut {
-    double ratio;
+    real ratio;
     unsigned q;
     unsigned flags;
     Rgba sc; // valid when flags & NODE_HAS_SC
@@ -146,37 +172,37 @@ struct ShadeOut {
 // with a uniform reflection ratio and the identity threshold direction (the host routes the bins).
 template <int D>
 struct ShadeDecision {
-    double ratio;
+    real ratio;
     unsigned q;
     unsigned flags;
     bool t_emit, r_emit;
     int dest;          // entity the transmitted ray continues in (valid when t_emit)
-    double from_theta; // angle_between(direction, -normal_closer); Fresnel / Snell surfaces only
+    real from_theta; // angle_between(direction, -normal_closer); Fresnel / Snell surfaces only
     RefractionCache rc;
 };
 template <int D, bool GLASS>
-__device__ __forceinline__ void shade_decide(const SceneView& sv, double time_millis, int ent, bool exiting, double cos_raw,
-                                             double angle_raw, const Vec<D>& p, const Vec<D>& n_raw, ShadeDecision<D>& out,
+__device__ __forceinline__ void shade_decide(const SceneView& sv, real time_millis, int ent, bool exiting, real cos_raw,
+                                             real angle_raw, const Vec<D>& p, const Vec<D>& n_raw, ShadeDecision<D>& out,
                                              Rgba& sc_out) {
     const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
-    const double cos_closer = exiting ? -cos_raw : cos_raw;
+    const real cos_closer = exiting ? -cos_raw : cos_raw;
     const bool needs_theta = GLASS && (sf.ratio_op == EUCL_RATIO_FRESNEL || sf.thr_op == EUCL_THR_SNELL);
     // angle_between(direction, -normal_closer): when exiting, -normal_closer IS the raw normal and the angle is the stored one
 #if EUCL_ANGLE_REUSE
-    out.from_theta = needs_theta ? (exiting ? angle_raw : angle_from_cos(-cos_closer)) : 0.0;
+    out.from_theta = needs_theta ? (exiting ? angle_raw : angle_from_cos(-cos_closer)) : R(0.0);
 #else
-    out.from_theta = needs_theta ? angle_from_cos(-cos_closer) : 0.0;
+    out.from_theta = needs_theta ? angle_from_cos(-cos_closer) : R(0.0);
 #endif
-    out.rc = RefractionCache{needs_theta ? dm_sin(out.from_theta) : 0.0, 0.0, 0.0, false};
+    out.rc = RefractionCache{needs_theta ? dm_sin(out.from_theta) : R(0.0), R(0.0), R(0.0), false};
     // `.min(1).max(0)`: Rust min/max drop a NaN operand, so NaN -> 1
-    const double ratio = fmax(fmin(reflection_ratio<D, GLASS>(sf, out.from_theta, exiting, out.rc), 1.0), 0.0);
+    const real ratio = fmax(fmin(reflection_ratio<D, GLASS>(sf, out.from_theta, exiting, out.rc), R(1.0)), R(0.0));
     out.ratio = ratio;
     out.q = 0u;
     out.flags = 0u;
     out.t_emit = false;
     out.dest = -1;
     bool have_t = false;
-    if (!(ratio >= 1.0)) { // get_intersection_color
+    if (!(ratio >= R(1.0))) { // get_intersection_color
         const Rgba sc = surface_color<D>(sv, sf, p, n_raw, cos_raw, angle_raw, exiting, time_millis);
         const unsigned q = to_pixel4(sc);
         out.q = q;
@@ -188,7 +214,7 @@ __device__ __forceinline__ void shade_decide(const SceneView& sv, double time_mi
             int dest = ent;
             if (exiting) {
                 const Vec<D> n_closer = -n_raw;
-                dest = material_at<D>(sv, p + (-n_closer) * kApproxEpsilon * 128.0);
+                dest = material_at<D>(sv, p + (-n_closer) * kApproxEpsilon * R(128.0));
             }
             if (dest >= 0) {
                 out.t_emit = true;
@@ -197,7 +223,7 @@ __device__ __forceinline__ void shade_decide(const SceneView& sv, double time_mi
             }
         }
     }
-    out.r_emit = !(ratio <= 0.0); // get_reflection_color
+    out.r_emit = !(ratio <= R(0.0)); // get_reflection_color
     if (!have_t && !out.r_emit) out.flags |= NODE_UNDEFINED | NODE_LEAF;
 }
 // Step 2: the child rays (surface.rs:84-100 transmitted, :119-139 reflected).
@@ -207,7 +233,7 @@ __device__ __forceinline__ void transmit_child(const SceneView& sv, const Vec<D>
     const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
     const Vec<D> n_closer = exiting ? -n_raw : n_raw;
     Vec<D> td = threshold_direction<D, GLASS>(sf, dir, n_closer, exiting, dec.from_theta, dec.rc);
-    out.o = p + (-n_closer) * kApproxEpsilon * 128.0;
+    out.o = p + (-n_closer) * kApproxEpsilon * R(128.0);
     material_exit<D>(sv, cur, td);
     material_enter<D>(sv, dec.dest, td);
     out.d = td;
@@ -217,15 +243,15 @@ template <int D>
 __device__ __forceinline__ void reflect_child(const Vec<D>& dir, int cur, bool exiting, const Vec<D>& p, const Vec<D>& n_raw,
                                               ChildRay<D>& out) {
     const Vec<D> n_closer = exiting ? -n_raw : n_raw;
-    out.o = p + n_closer * kApproxEpsilon * 128.0;
+    out.o = p + n_closer * kApproxEpsilon * R(128.0);
     out.d = reflection_direction<D>(dir, n_closer);
     out.cur = cur;
 }
 
 // Both steps at once (megakernel, which keeps the children on its own stack).
 template <int D, bool GLASS>
-__device__ __forceinline__ void shade_hit(const SceneView& sv, double time_millis, const Vec<D>& dir, int cur, int ent,
-                                          bool exiting, double cos_raw, double angle_raw, const Vec<D>& p, const Vec<D>& n_raw,
+__device__ __forceinline__ void shade_hit(const SceneView& sv, real time_millis, const Vec<D>& dir, int cur, int ent,
+                                          bool exiting, real cos_raw, real angle_raw, const Vec<D>& p, const Vec<D>& n_raw,
                                           ShadeOut<D>& out) {
     ShadeDecision<D> dec;
     shade_decide<D, GLASS>(sv, time_millis, ent, exiting, cos_raw, angle_raw, p, n_raw, dec, out.sc);
@@ -246,7 +272,7 @@ __device__ __forceinline__ Rgba transmit_over(unsigned q, const Rgba& child) {
 // trace_unknown tail (mod.rs:260-270) + to_pixel (mod.rs:342): composite over opaque white
 __device__ __forceinline__ void final_rgb8(const Rgba& fg, bool composite, uint8_t* out) {
     Rgba c = fg;
-    if (composite) c = from_premultiplied(over_pre(into_premultiplied(fg), Pre{1.0, 1.0, 1.0, 1.0}));
+    if (composite) c = from_premultiplied(over_pre(into_premultiplied(fg), Pre{R(1.0), R(1.0), R(1.0), R(1.0)}));
     out[0] = (uint8_t)channel_to_u8(c.r);
     out[1] = (uint8_t)channel_to_u8(c.g);
     out[2] = (uint8_t)channel_to_u8(c.b);
@@ -255,23 +281,23 @@ __device__ __forceinline__ void final_rgb8(const Rgba& fg, bool composite, uint8
 // Camera::get_ray_vector (d3/entity/camera.rs:164-185, d4/entity/camera.rs:155-176)
 template <int D>
 __device__ __forceinline__ Vec<D> camera_ray(const FrameParams& fp, int x, int y) {
-    const double rel_x = (double)(x - fp.width / 2) + (double)(1 - fp.width % 2) / 2.0;
-    const double rel_y = (double)(y - fp.height / 2) + (double)(1 - fp.height % 2) / 2.0;
+    const real rel_x = (real)(x - fp.width / 2) + (real)(1 - fp.width % 2) / R(2.0);
+    const real rel_y = (real)(y - fp.height / 2) + (real)(1 - fp.height % 2) / R(2.0);
     Vec<D> loc, center, up, right;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        loc[k] = fp.location[k];
-        center[k] = fp.center[k];
-        up[k] = fp.up[k];
-        right[k] = fp.right[k];
+        loc[k] = R(fp.location[k]);
+        center[k] = R(fp.center[k]);
+        up[k] = R(fp.up[k]);
+        right[k] = R(fp.right[k]);
     }
     const Vec<D> screen_point = center + (up * rel_y) + (right * rel_x);
     return normalize(screen_point - loc);
 }
 
 __device__ __forceinline__ Rgba checkerboard(int x, int y) { // mod.rs:387-395
-    if ((x / 8 + y / 8) % 2 == 0) return Rgba{0.0, 0.0, 0.0, 1.0};
-    return Rgba{1.0, 0.0, 1.0, 1.0};
+    if ((x / 8 + y / 8) % 2 == 0) return Rgba{R(0.0), R(0.0), R(0.0), R(1.0)};
+    return Rgba{R(1.0), R(0.0), R(1.0), R(1.0)};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,7 +310,7 @@ __global__ void __launch_bounds__(32) k_camera_entity(const uint8_t* __restrict_
     if (threadIdx.x == 0) {
         Vec<D> loc;
 #pragma unroll
-        for (int k = 0; k < D; ++k) loc[k] = fp.location[k];
+        for (int k = 0; k < D; ++k) loc[k] = R(fp.location[k]);
         *ws.cam_entity = material_at<D>(sv, loc);
     }
 }
@@ -296,7 +322,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
     const SceneView& sv = stage_scene(blob);
     Vec<D> loc;
 #pragma unroll
-    for (int k = 0; k < D; ++k) loc[k] = fp.location[k];
+    for (int k = 0; k < D; ++k) loc[k] = R(fp.location[k]);
     // material_at(camera location) is the same for every pixel of a frame: one thread per CTA evaluates it (a few hundred
     // instructions) instead of a kernel of its own in front of this one
     __shared__ int s_cam_entity;
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
         if (belongs_to < 0) { // the same for every pixel of the frame
             if (valid) {
                 store_res(ws, i, checkerboard(x, y));
-                ws.meta[i] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF | NODE_FINAL_RGB};
+                ws.meta[i] = NodeMeta{R(0.0), -1, -1, 0u, NODE_LEAF | NODE_FINAL_RGB};
                 ws.ray_cur[i] = -1;
                 if (hit_ids_out) hit_ids_out[(size_t)(cp.compact_rows ? local_row : y) * fp.width + x] = -2;
             }
@@ -358,15 +384,21 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
     __shared__ int s_rprefix[kRayBins + 1];
     const int off = ws.level_off[level], cnt = ws.count[level];
     const bool grouped = ws.ray_bins != 0;
-    if (threadIdx.x == 0) {
-        // no ray at all when the camera is in no entity (checkerboard frame, mod.rs:385-396)
+    // list sizes: one global load per thread, all in flight at once (a serial loop of dependent loads in front of every
+    // CTA's work was most of the fixed cost of a launch: ~10 us), then a prefix sum over shared memory
+    __shared__ int s_rcount[kRayBins];
+    if (threadIdx.x < kRayBins)
+        s_rcount[threadIdx.x] = (grouped && ((key_mask >> threadIdx.x) & 1u)) ? ws.rbin_count[level * kRayBins + threadIdx.x] : 0;
+    if (threadIdx.x == 32) // no ray at all when the camera is in no entity (checkerboard frame, mod.rs:385-396)
         s_skip = *ws.overflow != 0 || *ws.cam_entity < 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
         int acc = cnt;
         if (grouped) {
             acc = 0;
             for (int b = 0; b < kRayBins; ++b) {
                 s_rprefix[b] = acc;
-                if ((key_mask >> b) & 1u) acc += ws.rbin_count[level * kRayBins + b];
+                acc += s_rcount[b];
             }
             s_rprefix[kRayBins] = acc;
         }
@@ -377,7 +409,7 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
     const int total = s_total;
     if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
     const SceneView& sv = stage_scene(blob);
-    double* ts = plane_scratch(blob);
+    real* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
     const int stride = gridDim.x * blockDim.x;
     const int first = warp_first_position();
@@ -399,20 +431,20 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
         }
         int ent = -1;
         bool exiting_flag = false;
-        double cos_hint = 0.0;
+        real cos_hint = R(0.0);
         if (valid) {
             Vec<D> o, d;
             load_ray<D>(ws, node, o, d);
             const ClosestHit h = LIGHT ? closest_hit_light<D>(sv, o, d, ts, (int)blockDim.x) : closest_hit<D>(sv, o, d, ts, (int)blockDim.x);
-            HitHead rec{0.0, 0.0, 0.0, -1, 0};
+            HitHead rec{R(0.0), R(0.0), R(0.0), -1, 0};
             Vec<D> n;
 #pragma unroll
-            for (int k = 0; k < D; ++k) n[k] = 0.0;
+            for (int k = 0; k < D; ++k) n[k] = R(0.0);
             if (h.entity >= 0) { // orientation of the winner relative to the ray (mod.rs:114-125)
                 Vec<D> p;
                 hit_geometry<D>(sv, h.prim, h.flags, o, d, h.t, p, n);
-                const double cos_raw = angle_cos(d, n);
-                const double angle_raw = angle_from_cos(cos_raw);
+                const real cos_raw = angle_cos(d, n);
+                const real angle_raw = angle_from_cos(cos_raw);
                 const bool exiting = angle_raw < kFracPi2;
                 rec = HitHead{h.t, cos_raw, angle_raw, h.entity, exiting ? 1 : 0};
                 exiting_flag = exiting;
@@ -434,7 +466,7 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
                     const EuclSurface& sf = sv.surfaces()[sv.entities()[ent].surface];
                     if (sf.ratio_op == EUCL_RATIO_FRESNEL) {
                         // (from_index / to_index)^2 sin^2 > 1 with from = ratio_a, to = ratio_b when exiting; no division
-                        if (sf.ratio_a * sf.ratio_a * (1.0 - cos_hint * cos_hint) > sf.ratio_b * sf.ratio_b) cls = 2;
+                        if (R(sf.ratio_a) * R(sf.ratio_a) * (R(1.0) - cos_hint * cos_hint) > R(sf.ratio_b) * R(sf.ratio_b)) cls = 2;
                     }
                 }
                 const int key = ent < 0 ? 0 : 1 + kBinsPerEntity * ent + cls;
@@ -471,14 +503,20 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
     // be missing from the cooperative scene staging below (a partially staged scene = wild table offsets).
     __shared__ int s_skip, s_total;
     const bool binned = ws.n_bins > 1 && !last_level;
+    // bin sizes: one global load per thread, all in flight at once, then a prefix sum over shared memory (see k_intersect)
+    __shared__ int s_bcount[kMaxBins];
+    if (threadIdx.x < kMaxBins)
+        s_bcount[threadIdx.x] = (binned && (int)threadIdx.x < ws.n_bins && ((bin_mask >> threadIdx.x) & 1ull))
+                                    ? ws.bin_count[level * kMaxBins + threadIdx.x] : 0;
+    if (threadIdx.x == 64) s_skip = level > 0 && *ws.overflow != 0;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        s_skip = level > 0 && *ws.overflow != 0;
         int acc = cnt;
         if (binned) {
             acc = 0;
             for (int b = 0; b < ws.n_bins; ++b) {
                 s_prefix[b] = acc;
-                if ((bin_mask >> b) & 1ull) acc += ws.bin_count[level * kMaxBins + b];
+                acc += s_bcount[b];
             }
             s_prefix[ws.n_bins] = acc;
         }
@@ -523,7 +561,7 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
         if (valid) {
             Vec<D> o, d, n;
             load_ray<D>(ws, node, o, d);
-            HitHead ei{0.0, 0.0, 0.0, -1, 0};
+            HitHead ei{R(0.0), R(0.0), R(0.0), -1, 0};
             if (!last_level) ei = load_hit<D>(ws, node, n);
             if (level == 0 && hit_ids_out) {
                 const int local_row = cp.local_row0 + i / fp.width;
@@ -532,17 +570,17 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
             }
             if (ei.entity < 0) {
                 store_res(ws, node, mapped_color<D>(sv, sv.background, d)); // background.get_color(direction.to_point())
-                ws.meta[node] = NodeMeta{0.0, -1, -1, 0u, NODE_LEAF};
+                ws.meta[node] = NodeMeta{R(0.0), -1, -1, 0u, NODE_LEAF};
             } else {
                 const Vec<D> p = o + d * ei.t; // the intersectors' expression for the hit location (shape.rs:700,795,993)
                 Rgba sc;
-                shade_decide<D, GLASS>(sv, fp.time_millis, ei.entity, ei.exiting != 0, ei.cos_raw, ei.angle_raw, p, n, dec, sc);
+                shade_decide<D, GLASS>(sv, R(fp.time_millis), ei.entity, ei.exiting != 0, ei.cos_raw, ei.angle_raw, p, n, dec, sc);
                 if (dec.flags & NODE_HAS_SC) {
                     store_res(ws, node, sc);
                     if (!dec.r_emit) dec.flags |= NODE_LEAF; // opaque without a mirror term: the colour is final
                 }
                 if (dec.flags & NODE_UNDEFINED) {
-                    store_res(ws, node, Rgba{0.0, 0.0, 0.0, 0.0});
+                    store_res(ws, node, Rgba{R(0.0), R(0.0), R(0.0), R(0.0)});
                     atomicAdd(ws.undefined_count, 1ull);
                 }
                 shaded = true;
@@ -607,7 +645,29 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
     }
 }
 
-// K4: colour of the inner nodes of one level from the (already final) colours of level + 1.
+// Colour of a node from the (already final) colours of its children (surface.rs:104-114 transmitted, :150-161 combine).
+// Measured and not kept: resolving two levels per launch with the middle level's colours in registers (5 launches instead of
+// 10, a quarter less traffic, but a dependent chain of two gathers per thread): 3d_room 1.68 -> 2.03 ms, 4d_room 0.95 -> 1.06.
+__device__ __forceinline__ Rgba node_color(const Workspace& ws, const NodeMeta& m, int node) {
+    if (m.flags & NODE_LEAF) return load_res(ws, node);
+    bool have_t = false;
+    Rgba t{R(0.0), R(0.0), R(0.0), R(0.0)};
+    if (m.flags & NODE_HAS_SC) {
+        t = load_res(ws, node);
+        have_t = true;
+    } else if (m.tchild >= 0) {
+        t = transmit_over(m.q, load_res(ws, m.tchild));
+        have_t = true;
+    }
+    Rgba out = t;
+    if (m.rchild >= 0) {
+        const Rgba r = load_res(ws, m.rchild);
+        out = have_t ? combine_palette_color(r, t, (real)m.ratio) : r;
+    }
+    return out;
+}
+
+// K4: colour of the inner nodes of one level from the colours of level + 1.
 __global__ void __launch_bounds__(256) k_resolve(Workspace ws, int level) {
     if (*ws.overflow) return;
     const int off = ws.level_off[level], cnt = ws.count[level];
@@ -615,21 +675,7 @@ __global__ void __launch_bounds__(256) k_resolve(Workspace ws, int level) {
         const int node = off + i;
         const NodeMeta m = ws.meta[node];
         if (m.flags & NODE_LEAF) continue;
-        bool have_t = false;
-        Rgba t{0.0, 0.0, 0.0, 0.0};
-        if (m.flags & NODE_HAS_SC) {
-            t = load_res(ws, node);
-            have_t = true;
-        } else if (m.tchild >= 0) {
-            t = transmit_over(m.q, load_res(ws, m.tchild));
-            have_t = true;
-        }
-        Rgba out = t;
-        if (m.rchild >= 0) {
-            const Rgba r = load_res(ws, m.rchild);
-            out = have_t ? combine_palette_color(r, t, m.ratio) : r;
-        }
-        store_res(ws, node, out);
+        store_res(ws, node, node_color(ws, m, node));
     }
 }
 
@@ -638,25 +684,7 @@ __global__ void __launch_bounds__(256) k_final(FrameParams fp, ChunkParams cp, W
     if (*ws.overflow) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
         const NodeMeta m = ws.meta[i];
-        Rgba c;
-        if (m.flags & NODE_LEAF) {
-            c = load_res(ws, i);
-        } else {
-            bool have_t = false;
-            Rgba t{0.0, 0.0, 0.0, 0.0};
-            if (m.flags & NODE_HAS_SC) {
-                t = load_res(ws, i);
-                have_t = true;
-            } else if (m.tchild >= 0) {
-                t = transmit_over(m.q, load_res(ws, m.tchild));
-                have_t = true;
-            }
-            c = t;
-            if (m.rchild >= 0) {
-                const Rgba r = load_res(ws, m.rchild);
-                c = have_t ? combine_palette_color(r, t, m.ratio) : r;
-            }
-        }
+        const Rgba c = node_color(ws, m, i);
         const int local_row = cp.local_row0 + i / fp.width;
         const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
         final_rgb8(c, !(m.flags & NODE_FINAL_RGB), out_rgb8 + ((size_t)orow * fp.width + i % fp.width) * 3);
@@ -668,7 +696,7 @@ __global__ void __launch_bounds__(256) k_final(FrameParams fp, ChunkParams cp, W
 constexpr int kMegaMaxDepth = 24;
 template <int D>
 struct MegaFrame {
-    double ratio;
+    real ratio;
     unsigned q;
     unsigned state; // bit 0: waiting for the reflected child (else the transmitted one); bit 1: have T; bit 2: reflect pending
     Rgba t;
@@ -680,7 +708,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
                                                        Workspace ws, uint8_t* __restrict__ out_rgb8,
                                                        int32_t* __restrict__ hit_ids_out) {
     const SceneView& sv = stage_scene(blob);
-    double* ts = plane_scratch(blob);
+    real* ts = plane_scratch(blob);
     const int belongs_to = *ws.cam_entity;
     unsigned long long local_counts[kMegaMaxDepth + 1];
     for (int l = 0; l <= kMegaMaxDepth; ++l) local_counts[l] = 0ull;
@@ -698,11 +726,11 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
         MegaFrame<D> stack[kMegaMaxDepth];
         Vec<D> o, d;
 #pragma unroll
-        for (int k = 0; k < D; ++k) o[k] = fp.location[k];
+        for (int k = 0; k < D; ++k) o[k] = R(fp.location[k]);
         d = camera_ray<D>(fp, x, y);
         material_enter<D>(sv, belongs_to, d);
         int cur = belongs_to, level = 0;
-        Rgba val{0.0, 0.0, 0.0, 0.0};
+        Rgba val{R(0.0), R(0.0), R(0.0), R(0.0)};
         for (;;) {
             // ---- descend: evaluate the node for ray (o, d, cur) at `level`
             bool leaf = true;
@@ -710,16 +738,16 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
             int ent = -1;
             bool exiting = false;
             Vec<D> p, n;
-            double cos_raw = 0.0, angle_raw = 0.0;
+            real cos_raw = R(0.0), angle_raw = R(0.0);
             if (level < fp.max_depth) ent = intersect_ray<D>(sv, o, d, exiting, p, n, cos_raw, angle_raw, ts, (int)blockDim.x);
             if (level == 0 && hit_ids_out) hit_ids_out[opix] = ent;
             if (ent < 0) {
                 val = mapped_color<D>(sv, sv.background, d);
             } else {
                 ShadeOut<D> so;
-                shade_hit<D, true>(sv, fp.time_millis, d, cur, ent, exiting, cos_raw, angle_raw, p, n, so);
+                shade_hit<D, true>(sv, R(fp.time_millis), d, cur, ent, exiting, cos_raw, angle_raw, p, n, so);
                 if (so.flags & NODE_UNDEFINED) {
-                    val = Rgba{0.0, 0.0, 0.0, 0.0};
+                    val = Rgba{R(0.0), R(0.0), R(0.0), R(0.0)};
                     atomicAdd(ws.undefined_count, 1ull);
                 } else if (!so.t_emit && !so.r_emit) {
                     val = so.sc; // opaque, no mirror
@@ -796,15 +824,16 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
 // out: [0..D) location, [D..2D) direction, out_found: 1 ok, 0 start point in no entity, -1 step limit
 template <int D>
 __global__ void __launch_bounds__(32) k_trace_path(const uint8_t* __restrict__ blob, const double* __restrict__ in,
-                                                   double distance, double* __restrict__ out, int* __restrict__ out_found) {
+                                                   double distance_in, double* __restrict__ out, int* __restrict__ out_found) {
     const SceneView& sv = stage_scene(blob);
-    double* ts = plane_scratch(blob);
+    real* ts = plane_scratch(blob);
     if (threadIdx.x != 0) return;
+    real distance = R(distance_in);
     Vec<D> loc, dir;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        loc[k] = in[k];
-        dir[k] = in[D + k];
+        loc[k] = R(in[k]);
+        dir[k] = R(in[D + k]);
     }
     int belongs_to = material_at<D>(sv, loc);
     if (belongs_to < 0) {
@@ -816,12 +845,12 @@ __global__ void __launch_bounds__(32) k_trace_path(const uint8_t* __restrict__ b
     for (int step = 0; step < 100000; ++step) {
         const ClosestHit h = closest_hit<D>(sv, loc, dir, ts, (int)blockDim.x);
         bool moved = false;
-        if (h.entity >= 0 && !(distance - h.t <= 0.0)) { // get_path: Some
+        if (h.entity >= 0 && !(distance - h.t <= R(0.0))) { // get_path: Some
             Vec<D> p, n_raw;
             hit_geometry<D>(sv, h.prim, h.flags, loc, dir, h.t, p, n_raw);
             const bool exiting = angle_from_cos(angle_cos(dir, n_raw)) < kFracPi2;
             const Vec<D> n_closer = exiting ? -n_raw : n_raw;
-            const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * 128.0;
+            const Vec<D> new_origin = p + (-n_closer) * kApproxEpsilon * R(128.0);
             const int dest = exiting ? material_at<D>(sv, new_origin) : h.entity;
             if (dest >= 0) {
                 Vec<D> nd = dir;
@@ -849,6 +878,8 @@ __global__ void __launch_bounds__(32) k_trace_path(const uint8_t* __restrict__ b
     *out_found = found;
 }
 
+#if EUCL_REAL_IS_DOUBLE
+// BEGIN_KEEP64
 // FP64 issue-rate microbenchmark: 8 independent dependency chains per thread
 template <int OP>
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double seed) {
@@ -870,6 +901,8 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// END_KEEP64
+#endif
 inline int grid_for(int n, int block, int grid_max) {
     long long g = ((long long)n + block - 1) / block;
     if (g < 1) g = 1;
@@ -910,7 +943,7 @@ int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level) {
     // a light-capable scene without cull roots (every ray has key 0) runs the light build in node order
     const bool light_all = l.light_capable && l.n_cull == 0;
     const bool split = l.light_capable && ws.ray_bins != 0;
-    const size_t smem_light = l.smem_scene + sizeof(double) * kPlaneChainMax * kLightK2Block;
+    const size_t smem_light = l.smem_scene + sizeof(real) * kPlaneChainMax * kLightK2Block;
     const bool light = light_all || split, heavy = !light_all;
     const bool fork = light && heavy && l.side != nullptr;
     cudaStream_t light_stream = fork ? l.side : l.stream;
@@ -970,14 +1003,18 @@ int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkPar
     if (fork) join_side(l);
     return launches;
 }
-void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level) {
+// Bottom-up resolve of the ray tree (level max_depth holds leaves only) and the RGB8 pack of level 0.
+// Returns the number of kernels launched.
+int launch_resolve_and_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
+                             uint8_t* out_rgb8) {
     (void)dim;
-    k_resolve<<<l.grid_mem, 256, 0, l.stream>>>(ws, level);
-}
-void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
-                  uint8_t* out_rgb8) {
-    (void)dim;
+    int launches = 0;
+    for (int level = fp.max_depth - 1; level >= 1; --level) {
+        k_resolve<<<l.grid_mem, 256, 0, l.stream>>>(ws, level);
+        ++launches;
+    }
     k_final<<<grid_for(cp.n_pixels, 256, l.grid_mem), 256, 0, l.stream>>>(fp, cp, ws, out_rgb8);
+    return launches + 1;
 }
 void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
                        uint8_t* out_rgb8, int32_t* hit_ids_out) {
@@ -1022,7 +1059,7 @@ cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene) {
     EUCL_CONF(k_raygen<4>, smem_scene, 2);
     EUCL_CONF((k_intersect<3, false>), smem_bytes, heavy);
     EUCL_CONF((k_intersect<4, false>), smem_bytes, heavy);
-    const size_t smem_light = smem_scene + sizeof(double) * kPlaneChainMax * kLightK2Block;
+    const size_t smem_light = smem_scene + sizeof(real) * kPlaneChainMax * kLightK2Block;
     EUCL_CONF((k_intersect<3, true>), smem_light, EUCL_INTERSECT_LIGHT_MIN_BLOCKS);
     EUCL_CONF((k_intersect<4, true>), smem_light, EUCL_INTERSECT_LIGHT_MIN_BLOCKS);
     EUCL_CONF((k_shade<3, true, true>), smem_scene, kShadeResidentBlocks);
@@ -1041,6 +1078,8 @@ cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene) {
     return cudaSuccess;
 }
 
+#if EUCL_REAL_IS_DOUBLE
+// BEGIN_KEEP64
 int fp64_peak(double* dadd, double* dmul, double* dfma) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -1074,4 +1113,7 @@ int fp64_peak(double* dadd, double* dmul, double* dfma) {
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-} // namespace eucl
+// END_KEEP64
+#endif
+
+} // namespace EUCL_NS

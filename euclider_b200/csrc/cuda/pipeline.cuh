@@ -49,11 +49,9 @@ __host__ __device__ inline int frame_row_of_local(const ChunkParams& c, int loca
 //   [4 .. 4 + D)   the intersector's normal
 // The hit location is not stored: o + d * t from the ray record is the intersectors' own expression for it.
 // 64 bytes (3-D: one pad double): four 128-bit words, two whole DRAM sectors per gathered node.
-constexpr int kHitDoubles = 8;
-struct HitHead {
-    double t, cos_raw, angle_raw;
-    int32_t entity, exiting;
-};
+constexpr int kHitReals = 8;
+// reals per ray record: [origin, direction], padded to whole 16-byte words (f32, 3-D: 6 -> 8)
+__host__ __device__ constexpr int ray_reals(int dim, int real_bytes) { return real_bytes == 8 ? 2 * dim : 8; }
 
 // Ray-tree node record written by the shade kernel and consumed by the bottom-up resolve.
 struct NodeMeta {
@@ -79,11 +77,11 @@ enum : uint32_t {
 struct Workspace {
     int32_t capacity;   // nodes
     int32_t list_cap;   // entries per index list = the largest level the lists can hold
-    double* ray;        // [capacity][2 * D]: origin, direction
+    void* ray;          // [capacity][ray_reals] reals (f64 or f32 build): origin, direction
     int32_t* ray_cur;   // entity the ray travels in; -1 = no ray (checkerboard pixel)
-    double* hit;        // [capacity][kHitDoubles]
+    void* hit;          // [capacity][kHitReals] reals
     NodeMeta* meta;
-    double* res;        // [capacity][4]: resolved colour r, g, b, a (one 32-byte sector)
+    void* res;          // [capacity][4] reals: resolved colour r, g, b, a
     int32_t* count;     // [EUCL_MAX_LEVELS + 1] nodes per level
     int32_t* level_off; // [EUCL_MAX_LEVELS + 1] first node id of each level
     int32_t* overflow;  // 1: a child could not be appended (arena); 3: a level outgrew the index lists; 2: internal error
@@ -152,20 +150,27 @@ constexpr int kRayBins = 16; // 2^4 reach keys
 constexpr int kBinsPerEntity = 3; // entering, exiting, exiting with total internal reflection predicted
 constexpr int kMaxBins = 64; // shade-coherence bins (miss, then kBinsPerEntity per entity); larger scenes shade unbinned
 
-// kernels.cu
-void launch_camera_entity(int dim, const Launch& l, const FrameParams& fp, const Workspace& ws);
-void launch_raygen(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
-                   int32_t* hit_ids_out);
-int launch_intersect(int dim, const Launch& l, const Workspace& ws, int level); // returns the number of kernels launched
-int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws, int level,
-                 int32_t* hit_ids_out); // returns the number of kernels launched (light and / or heavy build)
-void launch_resolve(int dim, const Launch& l, const Workspace& ws, int level);
-void launch_final(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
-                  uint8_t* out_rgb8);
-void launch_megakernel(int dim, const Launch& l, const FrameParams& fp, const ChunkParams& cp, const Workspace& ws,
-                       uint8_t* out_rgb8, int32_t* hit_ids_out);
-void launch_trace_path(int dim, const Launch& l, const double* d_in, double distance, double* d_out, int* d_found);
-cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene);
-int fp64_peak(double* dadd, double* dmul, double* dfma); // T op/s on the current device
+} // namespace eucl
 
+// kernels.cu, compiled twice: namespace eucl (real = double) and namespace eucl_f32 (real = float, the reference's
+// `low_precision` feature).  The structs above are shared.
+#define EUCL_DECLARE_LAUNCHERS(NS)                                                                                             \
+    namespace NS {                                                                                                             \
+    void launch_camera_entity(int dim, const eucl::Launch& l, const eucl::FrameParams& fp, const eucl::Workspace& ws);        \
+    void launch_raygen(int dim, const eucl::Launch& l, const eucl::FrameParams& fp, const eucl::ChunkParams& cp,              \
+                       const eucl::Workspace& ws, int32_t* hit_ids_out);                                                       \
+    int launch_intersect(int dim, const eucl::Launch& l, const eucl::Workspace& ws, int level);                                \
+    int launch_shade(int dim, const eucl::Launch& l, const eucl::FrameParams& fp, const eucl::ChunkParams& cp,                \
+                     const eucl::Workspace& ws, int level, int32_t* hit_ids_out);                                              \
+    int launch_resolve_and_final(int dim, const eucl::Launch& l, const eucl::FrameParams& fp, const eucl::ChunkParams& cp,    \
+                                 const eucl::Workspace& ws, uint8_t* out_rgb8);                                                \
+    void launch_megakernel(int dim, const eucl::Launch& l, const eucl::FrameParams& fp, const eucl::ChunkParams& cp,          \
+                           const eucl::Workspace& ws, uint8_t* out_rgb8, int32_t* hit_ids_out);                                \
+    void launch_trace_path(int dim, const eucl::Launch& l, const double* d_in, double distance, double* d_out, int* d_found); \
+    cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene);                                                       \
+    }
+EUCL_DECLARE_LAUNCHERS(eucl)
+EUCL_DECLARE_LAUNCHERS(eucl_f32)
+namespace eucl {
+int fp64_peak(double* dadd, double* dmul, double* dfma); // T op/s on the current device (f64 build only)
 } // namespace eucl

@@ -84,11 +84,13 @@ class Environment:
 
     def __init__(self, parsed_handle: int, texture_paths: Sequence[str]):
         self._parsed = C.c_void_p(parsed_handle)
-        self._scenes: Dict[int, C.c_void_p] = {}
+        self._scenes: Dict[Tuple[int, str], C.c_void_p] = {}
         self.texture_paths = list(texture_paths)
         flat = lib().eucl_parsed_flat(self._parsed)
         self.camera: EuclCamera = flat.contents.camera.copy()  # pose the JSON constructs; mutable by the caller
         self.pipeline = EUCL_PIPELINE_WAVEFRONT
+        # the reference's scalar type F: "f64" (default build) or "f32" (cargo feature `low_precision`, src/main.rs:46-49)
+        self.precision = "f64"
 
     # -- reference API ---------------------------------------------------------------------------
     def max_depth(self) -> int:
@@ -189,11 +191,16 @@ class Environment:
         return int(self.flat.dim)
 
     def _device_scene(self, device: int) -> C.c_void_p:
-        if device not in self._scenes:
+        key = (device, self.precision)
+        if key not in self._scenes:
+            if self.precision not in ("f64", "f32"):
+                raise ValueError("precision must be 'f64' or 'f32'")
             handle = C.c_void_p()
-            check(lib().eucl_scene_create(lib().eucl_parsed_flat(self._parsed), device, C.byref(handle)))
-            self._scenes[device] = handle
-        return self._scenes[device]
+            check(lib().eucl_scene_create_precision(lib().eucl_parsed_flat(self._parsed), device,
+                                                    _capi.EUCL_PRECISION_F32 if self.precision == "f32" else _capi.EUCL_PRECISION_F64,
+                                                    C.byref(handle)))
+            self._scenes[key] = handle
+        return self._scenes[key]
 
     def set_texture(self, slot: int, width: int, height: int, rgba8: bytes) -> None:
         """Fills texture slot `slot` with decoded RGBA8 pixels (row 0 = top); for callers that decode

@@ -288,6 +288,13 @@ const char* eucl_version(void);
 
 /* The flat scene is borrowed for the duration of the call only. */
 int eucl_scene_create(const EuclFlatScene* flat, int device, EuclScene** out);
+
+/* The reference's scalar type `F` (src/main.rs:46-49): f64 by default, f32 with its cargo feature `low_precision`
+ * (Cargo.toml:19-21).  An f32 scene runs the same kernels compiled for float: geometry, colours and the node arena
+ * are f32, LinearSpace expressions stay f64 (meval), scene tables are narrowed where they are read.  Its pictures are
+ * compared with the f32 build of the test oracle, not with the f64 ones. */
+typedef enum EuclPrecision { EUCL_PRECISION_F64 = 0, EUCL_PRECISION_F32 = 1 } EuclPrecision;
+int eucl_scene_create_precision(const EuclFlatScene* flat, int device, int precision, EuclScene** out);
 void eucl_scene_destroy(EuclScene* scene);
 
 /* Run this scene's kernels on the caller's CUDA stream (a cudaStream_t, e.g. torch's current

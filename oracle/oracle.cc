@@ -30,6 +30,18 @@
 #include "euclider_b200.h"
 #include "eucl_detmath.h"
 
+// BEGIN_KEEP64
+// The reference's scalar type `F` (src/main.rs:46-49): f64, or f32 with its `low_precision` feature
+// (-DORACLE_F32: liboracle_f32.so).  Scene tables, the camera's JSON pose and LinearSpace expressions stay f64
+// (JSON numbers parse as f64, meval evaluates in f64) and are narrowed with `as F` where the reference does.
+#ifdef ORACLE_F32
+typedef float real;
+#else
+typedef double real;
+#endif
+#define R(x) ((real)(x))
+// END_KEEP64
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -51,7 +63,8 @@ static thread_local uint64_t g_flops = 0;
 //   liboracle.so      (default)           : the host's glibc -- what the Rust binary would link here
 //   liboracle_det.so  (-DORACLE_DETMATH)  : include/eucl_detmath.h, the fdlibm-style libm the CUDA
 //                                           path uses, for BIT-EXACT comparison with the GPU
-namespace om {
+// BEGIN_KEEP64
+namespace om64 {
 #ifdef ORACLE_DETMATH
 inline double acos(double x) { FLOPS(1); return eucl_det::det_acos(x); }
 inline double asin(double x) { FLOPS(1); return eucl_det::det_asin(x); }
@@ -67,25 +80,36 @@ inline double cos(double x) { FLOPS(1); return std::cos(x); }
 inline double atan(double x) { FLOPS(1); return std::atan(x); }
 inline double atan2(double y, double x) { FLOPS(1); return std::atan2(y, x); }
 #endif
+} // namespace om64
+// `real` flavour: evaluated in f64 and narrowed (f32 build: what a good acosf returns in all but rare halfway cases; the
+// CUDA f32 kernels do exactly the same, so the two agree bit for bit)
+namespace om {
+inline real acos(real x) { return (real)om64::acos((double)x); }
+inline real asin(real x) { return (real)om64::asin((double)x); }
+inline real sin(real x) { return (real)om64::sin((double)x); }
+inline real cos(real x) { return (real)om64::cos((double)x); }
+inline real atan(real x) { return (real)om64::atan((double)x); }
+inline real atan2(real y, real x) { return (real)om64::atan2((double)y, (double)x); }
 } // namespace om
+// END_KEEP64
 
-constexpr double PI = 3.14159265358979323846264338327950288;     // BaseFloat::pi()
-constexpr double FRAC_PI_2 = 1.57079632679489661923132169163975144; // BaseFloat::frac_pi_2()
-constexpr double APPROX_EPSILON = 1.0e-6; // nalgebra 0.8.2 ApproxEq::approx_epsilon (RECOLLECTION)
+constexpr real PI = R(3.14159265358979323846264338327950288);     // BaseFloat::pi()
+constexpr real FRAC_PI_2 = R(1.57079632679489661923132169163975144); // BaseFloat::frac_pi_2()
+constexpr real APPROX_EPSILON = R(1.0e-6); // nalgebra 0.8.2 ApproxEq::approx_epsilon (RECOLLECTION)
 
 // ---------------------------------------------------------------------------------------------
 // nalgebra 0.8 vector semantics: component-wise loops, dot = left-to-right sum in index order,
 // normalize = v / norm(v)
 template <int D>
 struct Vec {
-    double c[D];
-    double& operator[](int k) { return c[k]; }
-    double operator[](int k) const { return c[k]; }
+    real c[D];
+    real& operator[](int k) { return c[k]; }
+    real operator[](int k) const { return c[k]; }
 };
 template <int D>
-Vec<D> load(const double* p) {
+Vec<D> load(const double* p) { // scene tables and poses are f64: `as F`
     Vec<D> r;
-    for (int k = 0; k < D; ++k) r[k] = p[k];
+    for (int k = 0; k < D; ++k) r[k] = (real)p[k];
     return r;
 }
 template <int D>
@@ -109,30 +133,30 @@ Vec<D> operator-(const Vec<D>& a) {
     return r;
 }
 template <int D>
-Vec<D> operator*(const Vec<D>& a, double s) {
+Vec<D> operator*(const Vec<D>& a, real s) {
     Vec<D> r;
     FLOPS(D);
     for (int k = 0; k < D; ++k) r[k] = a[k] * s;
     return r;
 }
 template <int D>
-Vec<D> operator/(const Vec<D>& a, double s) {
+Vec<D> operator/(const Vec<D>& a, real s) {
     Vec<D> r;
     FLOPS(D);
     for (int k = 0; k < D; ++k) r[k] = a[k] / s;
     return r;
 }
 template <int D>
-double dot(const Vec<D>& a, const Vec<D>& b) {
+real dot(const Vec<D>& a, const Vec<D>& b) {
     FLOPS(2 * D - 1);
-    double s = a[0] * b[0];
+    real s = a[0] * b[0];
     for (int k = 1; k < D; ++k) s = s + a[k] * b[k];
     return s;
 }
 template <int D>
-double norm_squared(const Vec<D>& a) { return dot(a, a); }
+real norm_squared(const Vec<D>& a) { return dot(a, a); }
 template <int D>
-double norm(const Vec<D>& a) {
+real norm(const Vec<D>& a) {
     FLOPS(1);
     return std::sqrt(norm_squared(a));
 }
@@ -141,26 +165,26 @@ Vec<D> normalize(const Vec<D>& a) { return a / norm(a); }
 
 // util.rs:712-722
 template <int D>
-double angle_between(const Vec<D>& a, const Vec<D>& b) {
+real angle_between(const Vec<D>& a, const Vec<D>& b) {
     FLOPS(2); // *, / (the acos counts itself)
-    double result = om::acos(dot(a, b) / (norm(a) * norm(b)));
-    return std::isnan(result) ? 0.0 : result;
+    real result = om::acos(dot(a, b) / (norm(a) * norm(b)));
+    return std::isnan(result) ? R(0.0) : result;
 }
 
 // Rust f64::signum
-double rust_signum(double x) {
+real rust_signum(real x) {
     if (std::isnan(x)) return x;
-    return std::signbit(x) ? -1.0 : 1.0;
+    return std::signbit(x) ? -R(1.0) : R(1.0);
 }
 // Rust f64::min / f64::max (ignore a NaN operand)
-double rust_min(double a, double b) { return std::fmin(a, b); }
-double rust_max(double a, double b) { return std::fmax(a, b); }
+real rust_min(real a, real b) { return std::fmin(a, b); }
+real rust_max(real a, real b) { return std::fmax(a, b); }
 
 // util.rs:287-299
-double remainder_f(double a, double b) {
-    double rem = std::fmod(a, b);
-    if (rem == 0.0) return 0.0;
-    if (a < 0.0) return b + rem;
+real remainder_f(real a, real b) {
+    real rem = std::fmod(a, b);
+    if (rem == R(0.0)) return R(0.0);
+    if (a < R(0.0)) return b + rem;
     return rem;
 }
 int64_t remainder_i(int64_t a, int64_t b) {
@@ -173,9 +197,9 @@ int64_t remainder_i(int64_t a, int64_t b) {
 // ---------------------------------------------------------------------------------------------
 // palette 0.2.1 (RECOLLECTION): linear RGBA, no gamma on this path
 struct Rgba {
-    double r, g, b, a;
+    real r, g, b, a;
 };
-double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+real clamp01(real v) { return v < R(0.0) ? R(0.0) : (v > R(1.0) ? R(1.0) : v); }
 
 struct Counters {
     uint64_t nan_channel = 0; // App. A.6: NaN colour channel reaching to_pixel (reference panics)
@@ -184,12 +208,12 @@ struct Counters {
     uint64_t csg_runaway = 0;  // a CSG stream that never terminates (reference hangs)
 };
 
-uint8_t channel_to_u8(double c, Counters* cn) {
+uint8_t channel_to_u8(real c, Counters* cn) {
     if (std::isnan(c)) { // reference: to_u8().unwrap() panics; defined here as 0 and counted
         if (cn) cn->nan_channel++;
         return 0;
     }
-    return (uint8_t)(clamp01(c) * 255.0); // truncation
+    return (uint8_t)(clamp01(c) * R(255.0)); // truncation
 }
 void to_pixel4(const Rgba& c, uint8_t out[4], Counters* cn) {
     out[0] = channel_to_u8(c.r, cn);
@@ -198,72 +222,72 @@ void to_pixel4(const Rgba& c, uint8_t out[4], Counters* cn) {
     out[3] = channel_to_u8(c.a, cn);
 }
 Rgba new_u8(const uint8_t p[4]) {
-    return Rgba{(double)p[0] / 255.0, (double)p[1] / 255.0, (double)p[2] / 255.0, (double)p[3] / 255.0};
+    return Rgba{(real)p[0] / R(255.0), (real)p[1] / R(255.0), (real)p[2] / R(255.0), (real)p[3] / R(255.0)};
 }
 struct Pre { // PreAlpha<Rgb>
-    double r, g, b, a;
+    real r, g, b, a;
 };
 Pre into_premultiplied(const Rgba& c) {
-    double a = clamp01(c.a);
+    real a = clamp01(c.a);
     return Pre{c.r * a, c.g * a, c.b * a, a};
 }
 Rgba from_premultiplied(const Pre& p) {
-    double a = clamp01(p.a);
+    real a = clamp01(p.a);
     if (std::isnormal(a)) return Rgba{p.r / a, p.g / a, p.b / a, a};
-    return Rgba{0.0, 0.0, 0.0, a};
+    return Rgba{R(0.0), R(0.0), R(0.0), a};
 }
 
 // Blend on premultiplied colours: `s` is self (source), `d` the argument (destination).
 // darken / difference / over are what the benchmark scenes use; the rest follow the W3C
 // compositing formulas palette implements.
 Pre blend_pre(int fn, const Pre& s, const Pre& d) {
-    const double sa = s.a, da = d.a;
-    double alpha = clamp01(sa + da - sa * da);
-    auto each = [&](double a, double b) -> double {
+    const real sa = s.a, da = d.a;
+    real alpha = clamp01(sa + da - sa * da);
+    auto each = [&](real a, real b) -> real {
         switch (fn) {
-        case EUCL_BLEND_OVER: return a + b * (1.0 - sa);
+        case EUCL_BLEND_OVER: return a + b * (R(1.0) - sa);
         case EUCL_BLEND_INSIDE: return a * da;
-        case EUCL_BLEND_OUTSIDE: return a * (1.0 - da);
-        case EUCL_BLEND_ATOP: return a * da + b * (1.0 - sa);
-        case EUCL_BLEND_XOR: return a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_OUTSIDE: return a * (R(1.0) - da);
+        case EUCL_BLEND_ATOP: return a * da + b * (R(1.0) - sa);
+        case EUCL_BLEND_XOR: return a * (R(1.0) - da) + b * (R(1.0) - sa);
         case EUCL_BLEND_PLUS: return a + b;
-        case EUCL_BLEND_MULTIPLY: return a * b + a * (1.0 - da) + b * (1.0 - sa);
+        case EUCL_BLEND_MULTIPLY: return a * b + a * (R(1.0) - da) + b * (R(1.0) - sa);
         case EUCL_BLEND_SCREEN: return a + b - a * b;
         case EUCL_BLEND_OVERLAY:
-            if (b * 2.0 <= da) return 2.0 * a * b + a * (1.0 - da) + b * (1.0 - sa);
-            return a * (1.0 + da) + b * (1.0 + sa) - 2.0 * a * b - da * sa;
-        case EUCL_BLEND_DARKEN: return rust_min(a * da, b * sa) + a * (1.0 - da) + b * (1.0 - sa);
-        case EUCL_BLEND_LIGHTEN: return rust_max(a * da, b * sa) + a * (1.0 - da) + b * (1.0 - sa);
+            if (b * R(2.0) <= da) return R(2.0) * a * b + a * (R(1.0) - da) + b * (R(1.0) - sa);
+            return a * (R(1.0) + da) + b * (R(1.0) + sa) - R(2.0) * a * b - da * sa;
+        case EUCL_BLEND_DARKEN: return rust_min(a * da, b * sa) + a * (R(1.0) - da) + b * (R(1.0) - sa);
+        case EUCL_BLEND_LIGHTEN: return rust_max(a * da, b * sa) + a * (R(1.0) - da) + b * (R(1.0) - sa);
         case EUCL_BLEND_DODGE:
-            if (a == sa && !std::isnormal(b)) return a * (1.0 - da);
-            if (a == sa) return sa * da + a * (1.0 - da) + b * (1.0 - sa);
-            return sa * da * rust_min(1.0, (b / da) * sa / (sa - a)) + a * (1.0 - da) + b * (1.0 - sa);
+            if (a == sa && !std::isnormal(b)) return a * (R(1.0) - da);
+            if (a == sa) return sa * da + a * (R(1.0) - da) + b * (R(1.0) - sa);
+            return sa * da * rust_min(R(1.0), (b / da) * sa / (sa - a)) + a * (R(1.0) - da) + b * (R(1.0) - sa);
         case EUCL_BLEND_BURN:
-            if (!std::isnormal(a) && b == da) return sa * da + b * (1.0 - sa);
-            if (!std::isnormal(a)) return b * (1.0 - sa);
-            return sa * da * (1.0 - rust_min(1.0, (1.0 - b / da) * sa / a)) + a * (1.0 - da) + b * (1.0 - sa);
+            if (!std::isnormal(a) && b == da) return sa * da + b * (R(1.0) - sa);
+            if (!std::isnormal(a)) return b * (R(1.0) - sa);
+            return sa * da * (R(1.0) - rust_min(R(1.0), (R(1.0) - b / da) * sa / a)) + a * (R(1.0) - da) + b * (R(1.0) - sa);
         case EUCL_BLEND_HARD_LIGHT:
-            if (a * 2.0 <= sa) return 2.0 * a * b + a * (1.0 - da) + b * (1.0 - sa);
-            return a * (1.0 + da) + b * (1.0 + sa) - 2.0 * a * b - da * sa;
+            if (a * R(2.0) <= sa) return R(2.0) * a * b + a * (R(1.0) - da) + b * (R(1.0) - sa);
+            return a * (R(1.0) + da) + b * (R(1.0) + sa) - R(2.0) * a * b - da * sa;
         case EUCL_BLEND_SOFT_LIGHT: {
-            double m = std::isnormal(da) ? b / da : 0.0;
-            if (a * 2.0 <= sa) return b * (sa + (2.0 * a - sa) * (1.0 - m)) + a * (1.0 - da) + b * (1.0 - sa);
-            if (b * 4.0 <= da) {
-                double m2 = m * m, m3 = m2 * m;
-                return da * (2.0 * a - sa) * (m3 * 16.0 - m2 * 12.0 - m * 3.0) + a - a * da + b;
+            real m = std::isnormal(da) ? b / da : R(0.0);
+            if (a * R(2.0) <= sa) return b * (sa + (R(2.0) * a - sa) * (R(1.0) - m)) + a * (R(1.0) - da) + b * (R(1.0) - sa);
+            if (b * R(4.0) <= da) {
+                real m2 = m * m, m3 = m2 * m;
+                return da * (R(2.0) * a - sa) * (m3 * R(16.0) - m2 * R(12.0) - m * R(3.0)) + a - a * da + b;
             }
-            return da * (2.0 * a - sa) * (std::sqrt(m) - m) + a - a * da + b;
+            return da * (R(2.0) * a - sa) * (std::sqrt(m) - m) + a - a * da + b;
         }
-        case EUCL_BLEND_DIFFERENCE: return a + b - 2.0 * rust_min(a * da, b * sa);
-        case EUCL_BLEND_EXCLUSION: return a + b - 2.0 * a * b;
+        case EUCL_BLEND_DIFFERENCE: return a + b - R(2.0) * rust_min(a * da, b * sa);
+        case EUCL_BLEND_EXCLUSION: return a + b - R(2.0) * a * b;
         }
         return a;
     };
     switch (fn) {
     case EUCL_BLEND_INSIDE: alpha = clamp01(sa * da); break;
-    case EUCL_BLEND_OUTSIDE: alpha = clamp01(sa * (1.0 - da)); break;
+    case EUCL_BLEND_OUTSIDE: alpha = clamp01(sa * (R(1.0) - da)); break;
     case EUCL_BLEND_ATOP: alpha = clamp01(da); break;
-    case EUCL_BLEND_XOR: alpha = clamp01(sa + da - 2.0 * sa * da); break;
+    case EUCL_BLEND_XOR: alpha = clamp01(sa + da - R(2.0) * sa * da); break;
     case EUCL_BLEND_PLUS: alpha = clamp01(sa + da); break;
     default: break;
     }
@@ -271,38 +295,38 @@ Pre blend_pre(int fn, const Pre& s, const Pre& d) {
 }
 
 // util.rs:265-285
-Rgba combine_palette_color(const Rgba& a, const Rgba& b, double a_ratio) {
-    if (a_ratio <= 0.0) return b;
-    if (a_ratio >= 1.0) return a;
-    return Rgba{a.r * a_ratio + b.r * (1.0 - a_ratio), a.g * a_ratio + b.g * (1.0 - a_ratio),
-                a.b * a_ratio + b.b * (1.0 - a_ratio), a.a * a_ratio + b.a * (1.0 - a_ratio)};
+Rgba combine_palette_color(const Rgba& a, const Rgba& b, real a_ratio) {
+    if (a_ratio <= R(0.0)) return b;
+    if (a_ratio >= R(1.0)) return a;
+    return Rgba{a.r * a_ratio + b.r * (R(1.0) - a_ratio), a.g * a_ratio + b.g * (R(1.0) - a_ratio),
+                a.b * a_ratio + b.b * (R(1.0) - a_ratio), a.a * a_ratio + b.a * (R(1.0) - a_ratio)};
 }
 
 // surface.rs:295-390: blend_function_ratio is combine_palette_color, the named ones go through
 // premultiplied alpha
-Rgba blend_rgba(int fn, double ratio, const Rgba& source, const Rgba& destination) {
+Rgba blend_rgba(int fn, real ratio, const Rgba& source, const Rgba& destination) {
     if (fn == EUCL_BLEND_RATIO) return combine_palette_color(source, destination, ratio);
     return from_premultiplied(blend_pre(fn, into_premultiplied(source), into_premultiplied(destination)));
 }
 
 // palette Hsv -> Rgb, hue in degrees
-void hsv_to_rgb(double hue_degrees, double saturation, double value, double rgb[3]) {
-    double deg = hue_degrees;
+void hsv_to_rgb(real hue_degrees, real saturation, real value, real rgb[3]) {
+    real deg = hue_degrees;
     if (std::isfinite(deg)) {
-        while (deg >= 360.0) deg = deg - 360.0;
-        while (deg < 0.0) deg = deg + 360.0;
+        while (deg >= R(360.0)) deg = deg - R(360.0);
+        while (deg < R(0.0)) deg = deg + R(360.0);
     }
-    double c = value * saturation;
-    double h = deg / 60.0;
-    double x = c * (1.0 - std::fabs(std::fmod(h, 2.0) - 1.0));
-    double m = value - c;
-    double r, g, b;
-    if (h >= 0.0 && h < 1.0) { r = c; g = x; b = 0.0; }
-    else if (h >= 1.0 && h < 2.0) { r = x; g = c; b = 0.0; }
-    else if (h >= 2.0 && h < 3.0) { r = 0.0; g = c; b = x; }
-    else if (h >= 3.0 && h < 4.0) { r = 0.0; g = x; b = c; }
-    else if (h >= 4.0 && h < 5.0) { r = x; g = 0.0; b = c; }
-    else { r = c; g = 0.0; b = x; }
+    real c = value * saturation;
+    real h = deg / R(60.0);
+    real x = c * (R(1.0) - std::fabs(std::fmod(h, R(2.0)) - R(1.0)));
+    real m = value - c;
+    real r, g, b;
+    if (h >= R(0.0) && h < R(1.0)) { r = c; g = x; b = R(0.0); }
+    else if (h >= R(1.0) && h < R(2.0)) { r = x; g = c; b = R(0.0); }
+    else if (h >= R(2.0) && h < R(3.0)) { r = R(0.0); g = c; b = x; }
+    else if (h >= R(3.0) && h < R(4.0)) { r = R(0.0); g = x; b = c; }
+    else if (h >= R(4.0) && h < R(5.0)) { r = x; g = R(0.0); b = c; }
+    else { r = c; g = R(0.0); b = x; }
     rgb[0] = r + m;
     rgb[1] = g + m;
     rgb[2] = b + m;
@@ -310,51 +334,51 @@ void hsv_to_rgb(double hue_degrees, double saturation, double value, double rgb[
 
 // ---------------------------------------------------------------------------------------------
 // noise 0.4.1 Perlin, 4-D (RECOLLECTION; see ASSUMPTIONS.md)
-void perlin_grad4(unsigned index, double g[4]) {
-    const double diag = 0.577350269189625764077083524672081875;
+void perlin_grad4(unsigned index, real g[4]) {
+    const real diag = R(0.577350269189625764077083524672081875);
     unsigned i = index % 32;
     unsigned zero_at = i / 8, signs = i % 8;
     int bit = 0;
     for (unsigned k = 0; k < 4; ++k) {
         if (k == zero_at) {
-            g[k] = 0.0;
+            g[k] = R(0.0);
         } else {
             g[k] = (signs >> bit) & 1u ? -diag : diag;
             ++bit;
         }
     }
 }
-double perlin4(const uint8_t perm[256], const double point[4]) {
-    double floored[4], near_d[4], far_d[4];
+real perlin4(const uint8_t perm[256], const real point[4]) {
+    real floored[4], near_d[4], far_d[4];
     long near_c[4], far_c[4];
     for (int k = 0; k < 4; ++k) {
         floored[k] = std::floor(point[k]);
         near_c[k] = (long)floored[k];
         far_c[k] = near_c[k] + 1;
         near_d[k] = point[k] - floored[k];
-        far_d[k] = near_d[k] - 1.0;
+        far_d[k] = near_d[k] - R(1.0);
     }
-    double total = 0.0;
+    real total = R(0.0);
     bool first = true;
     // corner order f0000, f1000, f0100, f1100, ... (x fastest)
     for (int corner = 0; corner < 16; ++corner) {
         long c[4];
-        double d[4];
+        real d[4];
         for (int k = 0; k < 4; ++k) {
             bool far = (corner >> k) & 1;
             c[k] = far ? far_c[k] : near_c[k];
             d[k] = far ? far_d[k] : near_d[k];
         }
-        double attn = 1.0 - (((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) + d[3] * d[3]);
-        double v = 0.0;
-        if (attn > 0.0) {
+        real attn = R(1.0) - (((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) + d[3] * d[3]);
+        real v = R(0.0);
+        if (attn > R(0.0)) {
             unsigned h = perm[(unsigned)(c[0] & 0xff)];
             h = perm[h ^ (unsigned)(c[1] & 0xff)];
             h = perm[h ^ (unsigned)(c[2] & 0xff)];
             h = perm[h ^ (unsigned)(c[3] & 0xff)];
-            double g[4];
+            real g[4];
             perlin_grad4(h, g);
-            double a2 = attn * attn;
+            real a2 = attn * attn;
             v = (a2 * a2) * (((d[0] * g[0] + d[1] * g[1]) + d[2] * g[2]) + d[3] * g[3]);
         }
         if (first) {
@@ -364,7 +388,7 @@ double perlin4(const uint8_t perm[256], const double point[4]) {
             total = total + v;
         }
     }
-    return total * 4.424369240215691;
+    return total * R(4.424369240215691);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -374,7 +398,7 @@ template <int D>
 struct Hit { // shape.rs:88-109 (the `direction` copy is the ray direction; kept by the caller)
     Vec<D> location;
     Vec<D> normal;
-    double distance;
+    real distance;
 };
 
 // --- primitives ------------------------------------------------------------------------
@@ -385,28 +409,28 @@ int intersect_prim(const EuclPrim& pr, const Vec<D>& location, const Vec<D>& dir
     case EUCL_PRIM_VOID: return 0; // shape.rs:622-631
     case EUCL_PRIM_SPHERE: { // shape.rs:652-731
         Vec<D> center = load<D>(pr.v0);
-        double radius = pr.s0;
+        real radius = R(pr.s0);
         Vec<D> rel = location - center;
-        double a = norm_squared(direction);
-        double b = 2.0 * dot(direction, rel);
-        double c = norm_squared(rel) - radius * radius;
-        double d = b * b - 4.0 * a * c;
+        real a = norm_squared(direction);
+        real b = R(2.0) * dot(direction, rel);
+        real c = norm_squared(rel) - radius * radius;
+        real d = b * b - R(4.0) * a * c;
         FLOPS(7); // reject stage, scalar part
-        if (d < 0.0) return 0;
+        if (d < R(0.0)) return 0;
         FLOPS(9); // sqrt, two roots
-        double d_sqrt = std::sqrt(d);
-        double t1 = (-b - d_sqrt) / (2.0 * a);
-        double t2 = (-b + d_sqrt) / (2.0 * a);
-        double t_first, t_second = 0.0;
+        real d_sqrt = std::sqrt(d);
+        real t1 = (-b - d_sqrt) / (R(2.0) * a);
+        real t2 = (-b + d_sqrt) / (R(2.0) * a);
+        real t_first, t_second = R(0.0);
         bool has_first = false, has_second = false;
-        if (t1 >= 0.0) {
+        if (t1 >= R(0.0)) {
             t_first = t1;
             has_first = true;
-            if (t2 >= 0.0) {
+            if (t2 >= R(0.0)) {
                 t_second = t2;
                 has_second = true;
             }
-        } else if (t2 >= 0.0) {
+        } else if (t2 >= R(0.0)) {
             t_first = t2;
             has_first = true;
         }
@@ -423,41 +447,41 @@ int intersect_prim(const EuclPrim& pr, const Vec<D>& location, const Vec<D>& dir
     case EUCL_PRIM_HYPERPLANE:
     case EUCL_PRIM_HALFSPACE: { // shape.rs:779-809, 843-870
         Vec<D> n = load<D>(pr.v0);
-        double t = -(dot(n, location) + pr.s0) / dot(n, direction);
+        real t = -(dot(n, location) + R(pr.s0)) / dot(n, direction);
         FLOPS(3);
-        if (t < 0.0) return 0; // NaN and +inf pass, as in the reference
+        if (t < R(0.0)) return 0; // NaN and +inf pass, as in the reference
         out[0].location = direction * t + location;
         out[0].normal = n;
         out[0].distance = t;
-        if (pr.kind == EUCL_PRIM_HALFSPACE) out[0].normal = out[0].normal * -pr.s1;
+        if (pr.kind == EUCL_PRIM_HALFSPACE) out[0].normal = out[0].normal * -R(pr.s1);
         return 1;
     }
     case EUCL_PRIM_CYLINDER: { // shape.rs:935-1027
         Vec<D> center = load<D>(pr.v0), axis = load<D>(pr.v1);
-        double radius = pr.s0;
+        real radius = R(pr.s0);
         Vec<D> a_vec = direction - axis * dot(direction, axis);
         Vec<D> delta_location = location - center;
         Vec<D> c_vec = delta_location - axis * dot(delta_location, axis);
-        double a = norm_squared(a_vec);
-        double b = (1.0 + 1.0) * dot(a_vec, c_vec);
-        double c = norm_squared(c_vec) - radius * radius;
-        double d = b * b - 4.0 * a * c;
+        real a = norm_squared(a_vec);
+        real b = (R(1.0) + R(1.0)) * dot(a_vec, c_vec);
+        real c = norm_squared(c_vec) - radius * radius;
+        real d = b * b - R(4.0) * a * c;
         FLOPS(7);
-        if (d < 0.0) return 0;
+        if (d < R(0.0)) return 0;
         FLOPS(9);
-        double d_sqrt = std::sqrt(d);
-        double t1 = (-b - d_sqrt) / (2.0 * a);
-        double t2 = (-b + d_sqrt) / (2.0 * a);
-        double t_first, t_second = 0.0;
+        real d_sqrt = std::sqrt(d);
+        real t1 = (-b - d_sqrt) / (R(2.0) * a);
+        real t2 = (-b + d_sqrt) / (R(2.0) * a);
+        real t_first, t_second = R(0.0);
         bool has_first = false, has_second = false;
-        if (t1 >= 0.0) {
+        if (t1 >= R(0.0)) {
             t_first = t1;
             has_first = true;
-            if (t2 >= 0.0) {
+            if (t2 >= R(0.0)) {
                 t_second = t2;
                 has_second = true;
             }
-        } else if (t2 >= 0.0) {
+        } else if (t2 >= R(0.0)) {
             t_first = t2;
             has_first = true;
         }
@@ -486,19 +510,19 @@ bool prim_inside(const EuclPrim& pr, const Vec<D>& point) {
     case EUCL_PRIM_SPHERE: {                // shape.rs:734-738
         Vec<D> center = load<D>(pr.v0);
         FLOPS(1);
-        return norm_squared(center - point) <= pr.s0 * pr.s0;
+        return norm_squared(center - point) <= R(pr.s0) * R(pr.s0);
     }
     case EUCL_PRIM_HYPERPLANE: return false; // shape.rs:812-817
     case EUCL_PRIM_HALFSPACE: {              // shape.rs:873-881
         FLOPS(1);
-        double result = dot(load<D>(pr.v0), point) + pr.s0;
-        return pr.s1 == rust_signum(result);
+        real result = dot(load<D>(pr.v0), point) + R(pr.s0);
+        return R(pr.s1) == rust_signum(result);
     }
     case EUCL_PRIM_CYLINDER: { // shape.rs:1030-1038
         Vec<D> center = load<D>(pr.v0), axis = load<D>(pr.v1);
         Vec<D> on_axis = axis * dot(axis, point - center) + center;
         FLOPS(1);
-        return norm_squared(point - on_axis) <= pr.s0 * pr.s0;
+        return norm_squared(point - on_axis) <= R(pr.s0) * R(pr.s0);
     }
     }
     return false;
@@ -509,7 +533,7 @@ template <int D>
 struct Tracer {
     const EuclFlatScene& s;
     EuclCamera cam;
-    double time_seconds;
+    double time_seconds; // f64 whatever `real` is: the Duration arithmetic of the reference is not generic over F
     uint32_t max_depth;
     Counters counters;
     uint64_t level_counts[EUCL_MAX_LEVELS] = {0};
@@ -742,6 +766,7 @@ struct Tracer {
     }
 
     // --- materials (material.rs) ------------------------------------------------------------
+    // BEGIN_KEEP64 (meval expressions are f64 in both precisions, material.rs:99-110)
     double eval_expr(int first, int len, const double* vars) const {
         double st[64];
         int sp = 0;
@@ -758,19 +783,19 @@ struct Tracer {
                 case EUCL_FN_ABS: r = std::fabs(x); break;
                 case EUCL_FN_EXP: r = std::exp(x); break;
                 case EUCL_FN_LN: r = std::log(x); break;
-                case EUCL_FN_SIN: r = om::sin(x); break;
-                case EUCL_FN_COS: r = om::cos(x); break;
+                case EUCL_FN_SIN: r = om64::sin(x); break;
+                case EUCL_FN_COS: r = om64::cos(x); break;
                 case EUCL_FN_TAN: r = std::tan(x); break;
-                case EUCL_FN_ASIN: r = om::asin(x); break;
-                case EUCL_FN_ACOS: r = om::acos(x); break;
-                case EUCL_FN_ATAN: r = om::atan(x); break;
+                case EUCL_FN_ASIN: r = om64::asin(x); break;
+                case EUCL_FN_ACOS: r = om64::acos(x); break;
+                case EUCL_FN_ATAN: r = om64::atan(x); break;
                 case EUCL_FN_SINH: r = std::sinh(x); break;
                 case EUCL_FN_COSH: r = std::cosh(x); break;
                 case EUCL_FN_TANH: r = std::tanh(x); break;
                 case EUCL_FN_FLOOR: r = std::floor(x); break;
                 case EUCL_FN_CEIL: r = std::ceil(x); break;
                 case EUCL_FN_ROUND: r = std::round(x); break;
-                case EUCL_FN_SIGNUM: r = rust_signum(x); break;
+                case EUCL_FN_SIGNUM: r = std::isnan(x) ? x : (std::signbit(x) ? -1.0 : 1.0); break;
                 }
                 st[sp - 1] = r;
                 break;
@@ -785,7 +810,7 @@ struct Tracer {
                 case EUCL_EX_REM: r = std::fmod(a, b); break;
                 case EUCL_EX_POW: r = std::pow(a, b); break;
                 case EUCL_EX_FUNC2:
-                    if (o.arg == EUCL_FN_ATAN2) r = om::atan2(a, b);
+                    if (o.arg == EUCL_FN_ATAN2) r = om64::atan2(a, b);
                     else if (o.arg == EUCL_FN_MAX) r = std::fmax(a, b);
                     else r = std::fmin(a, b);
                     break;
@@ -802,8 +827,9 @@ struct Tracer {
         double in[D];
         for (int k = 0; k < D; ++k) in[k] = v[k];
         for (int k = 0; k < D; ++k)
-            v[k] = inverse ? eval_expr(t.inv_first[k], t.inv_len[k], in) : eval_expr(t.fwd_first[k], t.fwd_len[k], in);
+            v[k] = (real)(inverse ? eval_expr(t.inv_first[k], t.inv_len[k], in) : eval_expr(t.fwd_first[k], t.fwd_len[k], in));
     }
+    // END_KEEP64
     void material_enter(int entity, Vec<D>& direction) const { // material.rs:133-137,150-154
         const EuclMaterial& m = s.materials[s.entities[entity].material];
         if (m.kind != EUCL_MAT_LINEAR_SPACE) return;
@@ -823,10 +849,10 @@ struct Tracer {
     }
 
     // --- textures (surface.rs:434-542, d3/entity/surface.rs:60-68, d4/entity/surface.rs:11-15)
-    Rgba texel(const EuclTexture& t, double xf, double yf) {
+    Rgba texel(const EuclTexture& t, real xf, real yf) {
         // `<u32 as NumCast>::from(f)`: Some(trunc) iff -1 < f < 2^32; the reference unwraps
         int64_t x = 0, y = 0;
-        if (!(xf > -1.0 && xf < 4294967296.0) || !(yf > -1.0 && yf < 4294967296.0)) {
+        if (!(xf > -R(1.0) && xf < R(4294967296.0)) || !(yf > -R(1.0) && yf < R(4294967296.0))) {
             counters.bad_texcoord++;
         } else {
             x = (int64_t)xf;
@@ -838,45 +864,45 @@ struct Tracer {
             y = 0;
         }
         const uint8_t* p = s.texels + t.texel_offset + 4 * ((size_t)y * t.width + (size_t)x);
-        return Rgba{(double)p[0], (double)p[1], (double)p[2], (double)p[3]};
+        return Rgba{(real)p[0], (real)p[1], (real)p[2], (real)p[3]};
     }
-    Rgba sample_texture(const EuclMappedTexture& mt, double u, double v) {
+    Rgba sample_texture(const EuclMappedTexture& mt, real u, real v) {
         const EuclTexture& t = s.textures[mt.texture];
-        double width = (double)t.width, height = (double)t.height;
+        real width = (real)t.width, height = (real)t.height;
         if (mt.filter == EUCL_TEX_NEAREST) { // surface.rs:434-451
-            double x = std::floor(u * width), y = std::floor(v * height);
-            if (!(x > -1.0 && x < 4294967296.0) || !(y > -1.0 && y < 4294967296.0)) {
+            real x = std::floor(u * width), y = std::floor(v * height);
+            if (!(x > -R(1.0) && x < R(4294967296.0)) || !(y > -R(1.0) && y < R(4294967296.0))) {
                 counters.bad_texcoord++;
-                x = 0.0;
-                y = 0.0;
+                x = R(0.0);
+                y = R(0.0);
             }
             int64_t xi = remainder_i((int64_t)x, (int64_t)t.width), yi = remainder_i((int64_t)y, (int64_t)t.height);
-            Rgba p = texel(t, (double)xi, (double)yi);
-            return Rgba{p.r / 255.0, p.g / 255.0, p.b / 255.0, p.a / 255.0};
+            Rgba p = texel(t, (real)xi, (real)yi);
+            return Rgba{p.r / R(255.0), p.g / R(255.0), p.b / R(255.0), p.a / R(255.0)};
         }
         // surface.rs:453-489
-        double x = u * width - 0.5, y = v * height - 0.5;
-        double offset_x = x - std::floor(x), offset_y = y - std::floor(y);
+        real x = u * width - R(0.5), y = v * height - R(0.5);
+        real offset_x = x - std::floor(x), offset_y = y - std::floor(y);
         Rgba px[4];
-        const double ox[4] = {0.0, 1.0, 0.0, 1.0}, oy[4] = {0.0, 0.0, 1.0, 1.0};
+        const real ox[4] = {R(0.0), R(1.0), R(0.0), R(1.0)}, oy[4] = {R(0.0), R(0.0), R(1.0), R(1.0)};
         for (int k = 0; k < 4; ++k) px[k] = texel(t, remainder_f(x + ox[k], width), remainder_f(y + oy[k], height));
-        auto mix = [&](double p0, double p1, double p2, double p3) {
-            return ((p0 * (1.0 - offset_x) + p1 * offset_x) * (1.0 - offset_y) +
-                    (p2 * (1.0 - offset_x) + p3 * offset_x) * offset_y) /
-                   255.0;
+        auto mix = [&](real p0, real p1, real p2, real p3) {
+            return ((p0 * (R(1.0) - offset_x) + p1 * offset_x) * (R(1.0) - offset_y) +
+                    (p2 * (R(1.0) - offset_x) + p3 * offset_x) * offset_y) /
+                   R(255.0);
         };
         return Rgba{mix(px[0].r, px[1].r, px[2].r, px[3].r), mix(px[0].g, px[1].g, px[2].g, px[3].g),
                     mix(px[0].b, px[1].b, px[2].b, px[3].b), mix(px[0].a, px[1].a, px[2].a, px[3].a)};
     }
     Rgba mapped_color(int mapped, const Vec<D>& point) {
-        if (mapped < 0) return Rgba{0.0, 0.0, 0.0, 0.0}; // MappedTextureTransparent
+        if (mapped < 0) return Rgba{R(0.0), R(0.0), R(0.0), R(0.0)}; // MappedTextureTransparent
         const EuclMappedTexture& mt = s.mapped_textures[mapped];
         // uv_sphere on the first three components (uv_derank drops w first)
         Vec<3> p;
-        for (int k = 0; k < 3; ++k) p[k] = point[k] - mt.center[k];
+        for (int k = 0; k < 3; ++k) p[k] = point[k] - R(mt.center[k]);
         p = normalize(p);
-        double u = 0.5 + om::atan2(p[1], p[0]) / (2.0 * PI);
-        double v = 0.5 - om::asin(p[2]) / PI;
+        real u = R(0.5) + om::atan2(p[1], p[0]) / (R(2.0) * PI);
+        real v = R(0.5) - om::asin(p[2]) / PI;
         return sample_texture(mt, u, v);
     }
 
@@ -891,10 +917,10 @@ struct Tracer {
     };
 
     // util.rs:631-666
-    Vec<D> general_rotation(const Vec<D>& self, const Vec<D>& other, double angle, const Vec<D>& v) const {
-        double original[D][D], result[D][D]; // [row][col]
+    Vec<D> general_rotation(const Vec<D>& self, const Vec<D>& other, real angle, const Vec<D>& v) const {
+        real original[D][D], result[D][D]; // [row][col]
         for (int r = 0; r < D; ++r)
-            for (int c = 0; c < D; ++c) original[r][c] = r == c ? 1.0 : 0.0;
+            for (int c = 0; c < D; ++c) original[r][c] = r == c ? R(1.0) : R(0.0);
         for (int r = 0; r < D; ++r) {
             original[r][0] = self[r];
             original[r][1] = other[r];
@@ -915,65 +941,65 @@ struct Tracer {
             col = normalize(col);
             for (int r = 0; r < D; ++r) result[r][i] = col[r];
         }
-        double rot[D][D];
+        real rot[D][D];
         for (int r = 0; r < D; ++r)
-            for (int c = 0; c < D; ++c) rot[r][c] = r == c ? 1.0 : 0.0;
+            for (int c = 0; c < D; ++c) rot[r][c] = r == c ? R(1.0) : R(0.0);
         rot[0][0] = om::cos(angle);
         rot[0][1] = -om::sin(angle);
         rot[1][0] = om::sin(angle);
         rot[1][1] = om::cos(angle);
         // result * (rotation_matrix * result.transpose()); nalgebra accumulates from zero
-        double tmp[D][D], q[D][D];
+        real tmp[D][D], q[D][D];
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) {
-                double acc = 0.0;
+                real acc = R(0.0);
                 for (int k = 0; k < D; ++k) acc = acc + rot[i][k] * result[j][k];
                 tmp[i][j] = acc;
             }
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) {
-                double acc = 0.0;
+                real acc = R(0.0);
                 for (int k = 0; k < D; ++k) acc = acc + result[i][k] * tmp[k][j];
                 q[i][j] = acc;
             }
         Vec<D> out;
         for (int i = 0; i < D; ++i) {
-            double acc = 0.0;
+            real acc = R(0.0);
             for (int j = 0; j < D; ++j) acc = acc + v[j] * q[i][j];
             out[i] = acc;
         }
         return out;
     }
 
-    double reflection_ratio(const EuclSurface& sf, const Context& c) const {
-        if (sf.ratio_op == EUCL_RATIO_UNIFORM) return c.exiting ? 0.0 : sf.ratio_a; // surface.rs:201-211
+    real reflection_ratio(const EuclSurface& sf, const Context& c) const {
+        if (sf.ratio_op == EUCL_RATIO_UNIFORM) return c.exiting ? R(0.0) : R(sf.ratio_a); // surface.rs:201-211
         // surface.rs:214-244
         Vec<D> normal = -c.normal_closer;
-        double from_theta = angle_between(c.direction, normal);
-        double from_index = c.exiting ? sf.ratio_a : sf.ratio_b;
-        double to_index = c.exiting ? sf.ratio_b : sf.ratio_a;
-        double to_theta = om::asin((from_index / to_index) * om::sin(from_theta));
-        if (std::isnan(to_theta)) return 1.0;
-        double product_1_s = from_index * om::cos(from_theta);
-        double product_2_s = to_index * om::cos(to_theta);
-        double product_1_p = from_index * om::cos(to_theta);
-        double product_2_p = to_index * om::cos(from_theta);
-        double rs = (product_1_s - product_2_s) / (product_1_s + product_2_s);
-        double rp = (product_1_p - product_2_p) / (product_1_p + product_2_p);
-        double reflectance_s = rs * rs, reflectance_p = rp * rp;
-        return (reflectance_s + reflectance_p) / (1.0 + 1.0);
+        real from_theta = angle_between(c.direction, normal);
+        real from_index = c.exiting ? R(sf.ratio_a) : R(sf.ratio_b);
+        real to_index = c.exiting ? R(sf.ratio_b) : R(sf.ratio_a);
+        real to_theta = om::asin((from_index / to_index) * om::sin(from_theta));
+        if (std::isnan(to_theta)) return R(1.0);
+        real product_1_s = from_index * om::cos(from_theta);
+        real product_2_s = to_index * om::cos(to_theta);
+        real product_1_p = from_index * om::cos(to_theta);
+        real product_2_p = to_index * om::cos(from_theta);
+        real rs = (product_1_s - product_2_s) / (product_1_s + product_2_s);
+        real rp = (product_1_p - product_2_p) / (product_1_p + product_2_p);
+        real reflectance_s = rs * rs, reflectance_p = rp * rp;
+        return (reflectance_s + reflectance_p) / (R(1.0) + R(1.0));
     }
     Vec<D> reflection_direction(const Context& c) const { // surface.rs:246-256
-        return c.normal_closer * -2.0 * dot(c.direction, c.normal_closer) + c.direction;
+        return c.normal_closer * -R(2.0) * dot(c.direction, c.normal_closer) + c.direction;
     }
     Vec<D> threshold_direction(const EuclSurface& sf, const Context& c) const {
         if (sf.thr_op == EUCL_THR_IDENTITY) return c.direction; // surface.rs:259-266
         // surface.rs:268-288
         Vec<D> normal = -c.normal_closer;
-        double from_theta = angle_between(c.direction, normal);
-        double modifier = c.exiting ? sf.thr_a : 1.0 / sf.thr_a;
-        double to_theta = om::asin(modifier * om::sin(from_theta));
-        double angle_delta = to_theta - from_theta;
+        real from_theta = angle_between(c.direction, normal);
+        real modifier = c.exiting ? R(sf.thr_a) : R(1.0) / R(sf.thr_a);
+        real to_theta = om::asin(modifier * om::sin(from_theta));
+        real angle_delta = to_theta - from_theta;
         return general_rotation(normal, c.direction, angle_delta, c.direction);
     }
 
@@ -983,53 +1009,53 @@ struct Tracer {
         for (int i = sf.color_first; i < sf.color_first + sf.color_len; ++i) {
             const EuclColorOp& op = s.color_ops[i];
             switch (op.op) {
-            case EUCL_COL_UNIFORM: stack[sp++] = Rgba{op.f[0], op.f[1], op.f[2], op.f[3]}; break;
+            case EUCL_COL_UNIFORM: stack[sp++] = Rgba{R(op.f[0]), R(op.f[1]), R(op.f[2]), R(op.f[3])}; break;
             case EUCL_COL_ILLUM_GLOBAL: { // surface.rs:410-422
-                Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
-                double original_angle = angle_between(c.normal_closer, c.direction);
-                double angle = PI - original_angle;
-                double ratio = angle / FRAC_PI_2;
+                Rgba light{R(op.f[0]), R(op.f[1]), R(op.f[2]), R(op.f[3])}, dark{R(op.f[4]), R(op.f[5]), R(op.f[6]), R(op.f[7])};
+                real original_angle = angle_between(c.normal_closer, c.direction);
+                real angle = PI - original_angle;
+                real ratio = angle / FRAC_PI_2;
                 stack[sp++] = combine_palette_color(dark, light, ratio);
                 break;
             }
             case EUCL_COL_ILLUM_DIR: { // surface.rs:392-408
-                Rgba light{op.f[0], op.f[1], op.f[2], op.f[3]}, dark{op.f[4], op.f[5], op.f[6], op.f[7]};
+                Rgba light{R(op.f[0]), R(op.f[1]), R(op.f[2]), R(op.f[3])}, dark{R(op.f[4]), R(op.f[5]), R(op.f[6]), R(op.f[7])};
                 Vec<D> light_direction = load<D>(&op.f[8]);
                 Vec<D> normal = c.hit.normal;
                 if (angle_between(c.direction, normal) > FRAC_PI_2) normal = -normal;
-                double angle = angle_between(normal, -light_direction);
-                double ratio = 1.0 - angle / PI;
+                real angle = angle_between(normal, -light_direction);
+                real ratio = R(1.0) - angle / PI;
                 stack[sp++] = combine_palette_color(dark, light, ratio);
                 break;
             }
             case EUCL_COL_PERLIN_HUE: { // d3/entity/surface.rs:22-40
                 // (time * 1000).as_secs() as f64 / 1000.0
-                double time_millis = std::floor(time_seconds * 1000.0) / 1000.0;
-                double size = op.f[0], speed = op.f[1];
-                double location[4] = {c.hit.location[0] / size, c.hit.location[1] / size, c.hit.location[2] / size,
+                real time_millis = (real)(std::floor(time_seconds * 1000.0) / 1000.0); // Cast::from(f64) (d3/entity/surface.rs:32)
+                real size = R(op.f[0]), speed = R(op.f[1]);
+                real location[4] = {c.hit.location[0] / size, c.hit.location[1] / size, c.hit.location[2] / size,
                                       time_millis * speed};
-                double value = perlin4(s.perlin_perm, location);
-                double rgb[3];
-                hsv_to_rgb(value * 360.0, 1.0, 1.0, rgb);
-                stack[sp++] = Rgba{rgb[0], rgb[1], rgb[2], 1.0};
+                real value = perlin4(s.perlin_perm, location);
+                real rgb[3];
+                hsv_to_rgb(value * R(360.0), R(1.0), R(1.0), rgb);
+                stack[sp++] = Rgba{rgb[0], rgb[1], rgb[2], R(1.0)};
                 break;
             }
             case EUCL_COL_TEXTURE: stack[sp++] = mapped_color(op.i0, c.hit.location); break; // surface.rs:536-542
             case EUCL_COL_BLEND: { // surface.rs:295-307
                 Rgba destination = stack[--sp];
                 Rgba source = stack[--sp];
-                stack[sp++] = blend_rgba(op.i0, op.f[0], source, destination);
+                stack[sp++] = blend_rgba(op.i0, R(op.f[0]), source, destination);
                 break;
             }
             }
         }
-        return sp > 0 ? stack[sp - 1] : Rgba{0.0, 0.0, 0.0, 0.0};
+        return sp > 0 ? stack[sp - 1] : Rgba{R(0.0), R(0.0), R(0.0), R(0.0)};
     }
 
     // mod.rs:85-147
     bool trace_closest(const Vec<D>& location, const Vec<D>& direction, Context* out) {
         bool have = false;
-        double closest_distance = 0.0;
+        real closest_distance = R(0.0);
         for (int e = 0; e < s.n_entities; ++e) {
             const EuclEntity& ent = s.entities[e];
             if (ent.surface < 0) continue; // the filter of mod.rs:158-160
@@ -1065,12 +1091,12 @@ struct Tracer {
         if (depth > 0 && trace_closest(location, direction, &c)) {
             if (primary_hit) *primary_hit = c.hit_entity;
             const EuclSurface& sf = s.surfaces[s.entities[c.hit_entity].surface];
-            double ratio = rust_max(rust_min(reflection_ratio(sf, c), 1.0), 0.0);
+            real ratio = rust_max(rust_min(reflection_ratio(sf, c), R(1.0)), R(0.0));
             const Vec<D> offset = c.normal_closer; // used as (+-n * eps) * 128
             // get_intersection_color
             bool have_intersection = false;
             Rgba intersection_color{0, 0, 0, 0};
-            if (!(ratio >= 1.0)) {
+            if (!(ratio >= R(1.0))) {
                 Rgba sc = surface_color(sf, c);
                 uint8_t data[4];
                 to_pixel4(sc, data, &counters);
@@ -1079,7 +1105,7 @@ struct Tracer {
                     have_intersection = true;
                 } else {
                     Vec<D> transitioned = threshold_direction(sf, c);
-                    Vec<D> new_origin = c.hit.location + (-offset) * APPROX_EPSILON * 128.0;
+                    Vec<D> new_origin = c.hit.location + (-offset) * APPROX_EPSILON * R(128.0);
                     int destination = c.exiting ? material_at(new_origin) : c.hit_entity;
                     if (destination >= 0) {
                         material_exit(belongs_to, transitioned);
@@ -1097,9 +1123,9 @@ struct Tracer {
             // get_reflection_color
             bool have_reflection = false;
             Rgba reflection_color{0, 0, 0, 0};
-            if (!(ratio <= 0.0)) {
+            if (!(ratio <= R(0.0))) {
                 Vec<D> rd = reflection_direction(c);
-                Vec<D> new_origin = c.hit.location + offset * APPROX_EPSILON * 128.0;
+                Vec<D> new_origin = c.hit.location + offset * APPROX_EPSILON * R(128.0);
                 reflection_color = trace(depth - 1, belongs_to, new_origin, rd, nullptr);
                 have_reflection = true;
             }
@@ -1118,14 +1144,14 @@ struct Tracer {
     }
 
     // Universe::trace_path (mod.rs:186-227) with Surface::get_path inlined (surface.rs:164-197)
-    void trace_path(double distance, int belongs_to, const Vec<D>& location, const Vec<D>& direction, int budget,
+    void trace_path(real distance, int belongs_to, const Vec<D>& location, const Vec<D>& direction, int budget,
                     Vec<D>* out_location, Vec<D>* out_direction, bool* runaway) {
         Context c;
         c.origin_entity = belongs_to;
         if (budget > 0 && trace_closest(location, direction, &c)) {
-            if (!(distance - c.hit.distance <= 0.0)) {
-                double new_distance = distance - c.hit.distance;
-                Vec<D> new_origin = c.hit.location + (-c.normal_closer) * APPROX_EPSILON * 128.0;
+            if (!(distance - c.hit.distance <= R(0.0))) {
+                real new_distance = distance - c.hit.distance;
+                Vec<D> new_origin = c.hit.location + (-c.normal_closer) * APPROX_EPSILON * R(128.0);
                 int destination = c.exiting ? material_at(new_origin) : c.hit_entity;
                 if (destination >= 0) {
                     Vec<D> transitioned = c.direction;
@@ -1146,7 +1172,7 @@ struct Tracer {
         *out_direction = new_direction;
     }
     // Universe::trace_path_unknown (mod.rs:273-286); false = None
-    bool trace_path_unknown(double distance, const Vec<D>& location, const Vec<D>& direction, Vec<D>* out_location,
+    bool trace_path_unknown(real distance, const Vec<D>& location, const Vec<D>& direction, Vec<D>* out_location,
                             Vec<D>* out_direction, bool* runaway) {
         int belongs_to = material_at(location);
         if (belongs_to < 0) return false;
@@ -1158,22 +1184,22 @@ struct Tracer {
 
     // camera (d3/entity/camera.rs:164-185,369-390; d4/entity/camera.rs:155-176)
     Vec<D> ray_vector(int x, int y, int width, int height) const {
-        double rel_x = (double)(x - width / 2) + (double)(1 - width % 2) / 2.0;
-        double rel_y = (double)(y - height / 2) + (double)(1 - height % 2) / 2.0;
-        double w = (double)width, h = (double)height;
+        real rel_x = (real)(x - width / 2) + (real)(1 - width % 2) / R(2.0);
+        real rel_y = (real)(y - height / 2) + (real)(1 - height % 2) / R(2.0);
+        real w = (real)width, h = (real)height;
         Vec<D> location = load<D>(cam.location), forward = load<D>(cam.forward), up = load<D>(cam.up), right;
         if (D == 3) {
             Vec<3> cr;
-            cr[0] = cam.forward[1] * cam.up[2] - cam.forward[2] * cam.up[1];
-            cr[1] = cam.forward[2] * cam.up[0] - cam.forward[0] * cam.up[2];
-            cr[2] = cam.forward[0] * cam.up[1] - cam.forward[1] * cam.up[0];
+            cr[0] = R(cam.forward[1]) * R(cam.up[2]) - R(cam.forward[2]) * R(cam.up[1]);
+            cr[1] = R(cam.forward[2]) * R(cam.up[0]) - R(cam.forward[0]) * R(cam.up[2]);
+            cr[2] = R(cam.forward[0]) * R(cam.up[1]) - R(cam.forward[1]) * R(cam.up[0]);
             cr = normalize(cr);
             for (int k = 0; k < 3; ++k) right[k] = cr[k];
         } else {
             right = -load<D>(cam.left);
         }
-        double fov_rad = PI * (double)cam.fov_deg / 180.0;
-        double distance = std::sqrt(w * w + h * h) / (2.0 * std::tan(fov_rad / 2.0));
+        real fov_rad = PI * (real)cam.fov_deg / R(180.0);
+        real distance = std::sqrt(w * w + h * h) / (R(2.0) * std::tan(fov_rad / R(2.0)));
         Vec<D> center = location + forward * distance;
         Vec<D> screen_point = center + (up * rel_y) + (right * rel_x);
         return normalize(screen_point - location);
@@ -1184,14 +1210,14 @@ struct Tracer {
         Vec<D> point = load<D>(cam.location);
         Vec<D> vector = ray_vector(x, y, width, height);
         int belongs_to = material_at(point);
-        double r, g, b;
+        real r, g, b;
         if (belongs_to >= 0) {
             Vec<D> transitioned = vector;
             material_enter(belongs_to, transitioned);
             int primary = -1;
             Rgba fg = trace(max_depth, belongs_to, point, transitioned, &primary);
             if (hit_id) *hit_id = primary;
-            Pre over = blend_pre(EUCL_BLEND_OVER, into_premultiplied(fg), into_premultiplied(Rgba{1.0, 1.0, 1.0, 1.0}));
+            Pre over = blend_pre(EUCL_BLEND_OVER, into_premultiplied(fg), into_premultiplied(Rgba{R(1.0), R(1.0), R(1.0), R(1.0)}));
             Rgba out = from_premultiplied(over);
             r = out.r;
             g = out.g;
@@ -1199,11 +1225,11 @@ struct Tracer {
         } else {
             if (hit_id) *hit_id = -2;
             if ((x / 8 + y / 8) % 2 == 0) {
-                r = g = b = 0.0;
+                r = g = b = R(0.0);
             } else {
-                r = 1.0;
-                g = 0.0;
-                b = 1.0;
+                r = R(1.0);
+                g = R(0.0);
+                b = R(1.0);
             }
         }
         rgb[0] = channel_to_u8(r, &counters);
@@ -1273,6 +1299,7 @@ int render_impl(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t w
 
 } // namespace
 
+// BEGIN_KEEP64
 extern "C" {
 
 // Renders rows [row_begin, row_end) of a width x height frame (row 0 = bottom) into out_rgb
@@ -1288,6 +1315,7 @@ int oracle_render(const EuclFlatScene* scene, const EuclCamera* camera, uint32_t
     return -1;
 }
 
+#ifndef ORACLE_F32 // the unit-test hooks probe the f64 build; liboracle_f32.so exports the renderer and the camera path only
 // --- unit-test hooks -------------------------------------------------------------------------
 
 // Full intersection stream of entity `entity` (up to the first None): out = n x (distance,
@@ -1348,6 +1376,8 @@ int oracle_prim_inside(int dim, const EuclPrim* prim, const double* point) {
     return prim_inside<4>(*prim, load<4>(point));
 }
 
+#endif
+
 // Universe::trace_path_unknown: returns 0 ok, 1 None (start point in no entity), -1 runaway
 int oracle_trace_path(const EuclFlatScene* scene, const double* location, const double* direction, double distance,
                       double* out_location, double* out_direction) {
@@ -1356,24 +1386,25 @@ int oracle_trace_path(const EuclFlatScene* scene, const double* location, const 
     if (scene->dim == 3) {
         Tracer<3> tr(*scene, cam, 0.0);
         Vec<3> l, d;
-        ok = tr.trace_path_unknown(distance, load<3>(location), load<3>(direction), &l, &d, &runaway);
+        ok = tr.trace_path_unknown((real)distance, load<3>(location), load<3>(direction), &l, &d, &runaway);
         for (int k = 0; ok && k < 3; ++k) {
-            out_location[k] = l[k];
-            out_direction[k] = d[k];
+            out_location[k] = (double)l[k];
+            out_direction[k] = (double)d[k];
         }
     } else {
         Tracer<4> tr(*scene, cam, 0.0);
         Vec<4> l, d;
-        ok = tr.trace_path_unknown(distance, load<4>(location), load<4>(direction), &l, &d, &runaway);
+        ok = tr.trace_path_unknown((real)distance, load<4>(location), load<4>(direction), &l, &d, &runaway);
         for (int k = 0; ok && k < 4; ++k) {
-            out_location[k] = l[k];
-            out_direction[k] = d[k];
+            out_location[k] = (double)l[k];
+            out_direction[k] = (double)d[k];
         }
     }
     if (runaway) return -1;
     return ok ? 0 : 1;
 }
 
+#ifndef ORACLE_F32
 int oracle_entity_inside(const EuclFlatScene* scene, int entity, const double* point) {
     EuclCamera cam{};
     if (scene->dim == 3) return Tracer<3>(*scene, cam, 0.0).node_inside(scene->entities[entity].node_root, load<3>(point));
@@ -1444,6 +1475,7 @@ void oracle_detmath_unary(int fn, const double* x, double* out, int n) {
 void oracle_detmath_atan2(const double* y, const double* x, double* out, int n) {
     for (int i = 0; i < n; ++i) out[i] = eucl_det::det_atan2(y[i], x[i]);
 }
+#endif
 int oracle_uses_detmath(void) {
 #ifdef ORACLE_DETMATH
     return 1;
@@ -1451,6 +1483,9 @@ int oracle_uses_detmath(void) {
     return 0;
 #endif
 }
+// bytes of the scalar type this build traces in (8: f64, 4: the reference's `low_precision` f32)
+int oracle_real_bytes(void) { return (int)sizeof(real); }
+#ifndef ORACLE_F32
 
 void oracle_hsv_to_rgb(double h, double s, double v, double* rgb) { hsv_to_rgb(h, s, v, rgb); }
 
@@ -1519,4 +1554,6 @@ void oracle_ray_vector(const EuclFlatScene* scene, const EuclCamera* cam, int x,
     }
 }
 
+#endif
 } // extern "C"
+// END_KEEP64

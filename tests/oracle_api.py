@@ -16,7 +16,8 @@ from euclider_b200._capi import EUCL_MAX_LEVELS, EuclCamera, EuclFlatScene, Eucl
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
 LIB_PATHS = {"glibc": ORACLE_DIR / "liboracle.so", "det": ORACLE_DIR / "liboracle_det.so",
-             "count": ORACLE_DIR / "liboracle_count.so"}  # "count": det + flop counters (tools/oracle_flops.py)
+             "count": ORACLE_DIR / "liboracle_count.so",  # "count": det + flop counters (tools/oracle_flops.py)
+             "f32": ORACLE_DIR / "liboracle_f32.so"}  # the reference's `low_precision` feature (type F = f32), det libm
 _libs = {}
 
 dptr = C.POINTER(C.c_double)
@@ -28,7 +29,8 @@ def build(target: str = "all") -> None:
 
 def lib(variant: str = "det") -> C.CDLL:
     """variant "det": transcendental functions from include/eucl_detmath.h (bit-comparable with the
-    CUDA path); "glibc": the host libm (what the Rust reference would link on this platform)."""
+    CUDA path); "glibc": the host libm (what the Rust reference would link on this platform); "f32": the `det` build
+    with `type F = f32` (renderer and camera path only: the unit-test hooks probe the f64 builds)."""
     if variant not in _libs:
         path = LIB_PATHS[variant]
         deps = [ORACLE_DIR / "oracle.cc", ROOT / "include" / "euclider_b200.h", ROOT / "include" / "eucl_detmath.h"]
@@ -38,53 +40,55 @@ def lib(variant: str = "det") -> C.CDLL:
         h.oracle_render.restype = C.c_int
         h.oracle_render.argtypes = [C.POINTER(EuclFlatScene), C.POINTER(EuclCamera), C.c_uint32, C.c_uint32, C.c_double,
                                     C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        h.oracle_entity_intersections.restype = C.c_int
-        h.oracle_entity_intersections.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr, dptr, C.c_int, dptr]
-        h.oracle_prim_intersect.restype = C.c_int
-        h.oracle_prim_intersect.argtypes = [C.c_int, C.POINTER(EuclPrim), dptr, dptr, dptr]
-        h.oracle_prim_inside.restype = C.c_int
-        h.oracle_prim_inside.argtypes = [C.c_int, C.POINTER(EuclPrim), dptr]
-        h.oracle_entity_inside.restype = C.c_int
-        h.oracle_entity_inside.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr]
-        h.oracle_material_at.restype = C.c_int
-        h.oracle_material_at.argtypes = [C.POINTER(EuclFlatScene), dptr]
-        h.oracle_angle_between.restype = C.c_double
-        h.oracle_angle_between.argtypes = [C.c_int, dptr, dptr]
-        h.oracle_angle_between_f32.restype = C.c_float
-        h.oracle_angle_between_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
-        h.oracle_combine_palette_color.restype = None
-        h.oracle_combine_palette_color.argtypes = [dptr, dptr, C.c_double, dptr]
-        h.oracle_combine_palette_color_f32.restype = None
-        h.oracle_combine_palette_color_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
-                                                       C.POINTER(C.c_float)]
-        h.oracle_remainder_i.restype = C.c_int64
-        h.oracle_remainder_i.argtypes = [C.c_int64, C.c_int64]
-        h.oracle_remainder_f.restype = C.c_double
-        h.oracle_remainder_f.argtypes = [C.c_double, C.c_double]
-        h.oracle_blend.restype = None
-        h.oracle_blend.argtypes = [C.c_int, C.c_double, dptr, dptr, dptr]
-        h.oracle_to_pixel.restype = None
-        h.oracle_to_pixel.argtypes = [dptr, C.POINTER(C.c_uint8)]
-        h.oracle_perlin4.restype = C.c_double
-        h.oracle_perlin4.argtypes = [C.POINTER(C.c_uint8), dptr]
-        h.oracle_hsv_to_rgb.restype = None
-        h.oracle_hsv_to_rgb.argtypes = [C.c_double, C.c_double, C.c_double, dptr]
-        h.oracle_general_rotation.restype = None
-        h.oracle_general_rotation.argtypes = [C.c_int, dptr, dptr, C.c_double, dptr, dptr]
-        h.oracle_surface_probe.restype = None
-        h.oracle_surface_probe.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr, dptr, C.c_int, dptr, dptr, dptr]
-        h.oracle_mapped_color.restype = None
-        h.oracle_mapped_color.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr, dptr]
-        h.oracle_ray_vector.restype = None
-        h.oracle_ray_vector.argtypes = [C.POINTER(EuclFlatScene), C.POINTER(EuclCamera), C.c_int, C.c_int, C.c_int,
-                                        C.c_int, dptr]
-        h.oracle_detmath_unary.restype = None
-        h.oracle_detmath_unary.argtypes = [C.c_int, dptr, dptr, C.c_int]
-        h.oracle_detmath_atan2.restype = None
-        h.oracle_detmath_atan2.argtypes = [dptr, dptr, dptr, C.c_int]
+        if variant != "f32":
+            h.oracle_entity_intersections.restype = C.c_int
+            h.oracle_entity_intersections.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr, dptr, C.c_int, dptr]
+            h.oracle_prim_intersect.restype = C.c_int
+            h.oracle_prim_intersect.argtypes = [C.c_int, C.POINTER(EuclPrim), dptr, dptr, dptr]
+            h.oracle_prim_inside.restype = C.c_int
+            h.oracle_prim_inside.argtypes = [C.c_int, C.POINTER(EuclPrim), dptr]
+            h.oracle_entity_inside.restype = C.c_int
+            h.oracle_entity_inside.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr]
+            h.oracle_material_at.restype = C.c_int
+            h.oracle_material_at.argtypes = [C.POINTER(EuclFlatScene), dptr]
+            h.oracle_angle_between.restype = C.c_double
+            h.oracle_angle_between.argtypes = [C.c_int, dptr, dptr]
+            h.oracle_angle_between_f32.restype = C.c_float
+            h.oracle_angle_between_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+            h.oracle_combine_palette_color.restype = None
+            h.oracle_combine_palette_color.argtypes = [dptr, dptr, C.c_double, dptr]
+            h.oracle_combine_palette_color_f32.restype = None
+            h.oracle_combine_palette_color_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                                                           C.POINTER(C.c_float)]
+            h.oracle_remainder_i.restype = C.c_int64
+            h.oracle_remainder_i.argtypes = [C.c_int64, C.c_int64]
+            h.oracle_remainder_f.restype = C.c_double
+            h.oracle_remainder_f.argtypes = [C.c_double, C.c_double]
+            h.oracle_blend.restype = None
+            h.oracle_blend.argtypes = [C.c_int, C.c_double, dptr, dptr, dptr]
+            h.oracle_to_pixel.restype = None
+            h.oracle_to_pixel.argtypes = [dptr, C.POINTER(C.c_uint8)]
+            h.oracle_perlin4.restype = C.c_double
+            h.oracle_perlin4.argtypes = [C.POINTER(C.c_uint8), dptr]
+            h.oracle_hsv_to_rgb.restype = None
+            h.oracle_hsv_to_rgb.argtypes = [C.c_double, C.c_double, C.c_double, dptr]
+            h.oracle_general_rotation.restype = None
+            h.oracle_general_rotation.argtypes = [C.c_int, dptr, dptr, C.c_double, dptr, dptr]
+            h.oracle_surface_probe.restype = None
+            h.oracle_surface_probe.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr, dptr, C.c_int, dptr, dptr, dptr]
+            h.oracle_mapped_color.restype = None
+            h.oracle_mapped_color.argtypes = [C.POINTER(EuclFlatScene), C.c_int, dptr, dptr]
+            h.oracle_ray_vector.restype = None
+            h.oracle_ray_vector.argtypes = [C.POINTER(EuclFlatScene), C.POINTER(EuclCamera), C.c_int, C.c_int, C.c_int,
+                                            C.c_int, dptr]
+            h.oracle_detmath_unary.restype = None
+            h.oracle_detmath_unary.argtypes = [C.c_int, dptr, dptr, C.c_int]
+            h.oracle_detmath_atan2.restype = None
+            h.oracle_detmath_atan2.argtypes = [dptr, dptr, dptr, C.c_int]
         h.oracle_trace_path.restype = C.c_int
         h.oracle_trace_path.argtypes = [C.POINTER(EuclFlatScene), dptr, dptr, C.c_double, dptr, dptr]
         h.oracle_uses_detmath.restype = C.c_int
+        h.oracle_real_bytes.restype = C.c_int
         _libs[variant] = h
     return _libs[variant]
 
