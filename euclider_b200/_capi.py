@@ -148,6 +148,7 @@ PROTOTYPES = {
     "eucl_camera_rotate_plane4": (C.c_int, [C.POINTER(EuclCamera), C.c_int, C.c_int, C.c_double]),
     "eucl_device_malloc": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "eucl_device_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "eucl_scene_memory": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "eucl_host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
     "eucl_host_unregister": (C.c_int, [C.c_void_p]),
     "eucl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

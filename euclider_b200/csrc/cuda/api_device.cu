@@ -1203,6 +1203,27 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     EUCL_CUDA(cudaEventRecord(s->ev[1], s->stream));
     EUCL_CUDA(cudaEventSynchronize(s->ev[1]));
     EUCL_CUDA(cudaEventElapsedTime(&st.ms_total, s->ev[0], s->ev[1]));
+    // A frame that had to grow its arena over-shot (capacity grows by half each retry).  Now that the frame's real node
+    // count is known, the scene keeps that plus a few per cent and gives the rest back: the next frame of this size
+    // allocates once more, exactly, and nothing afterwards.
+    if (st.retries > 0 && st.pixels > 0 && st.nodes > 0 && o->pipeline == EUCL_PIPELINE_WAVEFRONT && st.pixels == (uint64_t)my_rows * width) {
+        uint64_t max_level = 0;
+        for (uint32_t lv = 0; lv <= cam->max_depth; ++lv) max_level = std::max<uint64_t>(max_level, st.level_counts[lv]);
+        const double tight = (double)st.nodes / (double)st.pixels * 1.03 + 0.02;
+        const double tight_list = std::max(1.0, (double)max_level / (double)st.pixels * 1.03);
+        if ((double)s->arena_capacity > ((double)st.pixels * tight + 1024) * 1.08) {
+            s->arena_factor = tight;
+            s->list_factor = tight_list;
+            s->nodes.release();
+            s->order.release();
+            s->rorder.release();
+            s->arena_capacity = 0;
+            s->list_capacity = 0;
+            if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+            s->graph_exec = nullptr;
+            s->graph_key = s->seen_key = 0;
+        }
+    }
     if (s->ray_bins_mode < 0 && st.retries == 0 && my_rows > 0 && o->pipeline == EUCL_PIPELINE_WAVEFRONT) {
         if (s->n_cull == 0) {
             s->ray_bins_mode = 0;
@@ -1293,6 +1314,14 @@ int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
         if (want_hit) EUCL_CUDA(copy_bands(out_hit_ids, s->hit_ids.ptr, 4));
     }
     EUCL_CUDA(cudaStreamSynchronize(s->stream));
+    return EUCL_OK;
+}
+
+int eucl_scene_memory(const EuclScene* s, uint64_t* arena_bytes, uint64_t* list_bytes, uint64_t* node_capacity) {
+    if (!s) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_memory: null scene");
+    if (arena_bytes) *arena_bytes = (uint64_t)s->nodes.bytes;
+    if (list_bytes) *list_bytes = (uint64_t)(s->order.bytes + s->rorder.bytes);
+    if (node_capacity) *node_capacity = (uint64_t)s->arena_capacity;
     return EUCL_OK;
 }
 

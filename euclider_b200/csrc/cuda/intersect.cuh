@@ -14,7 +14,10 @@
 namespace EUCL_NS {
 using namespace eucl;
 
-constexpr int CSG_ARENA = 256;     // compact hits per thread (scene_create validates programs against it)
+#ifndef EUCL_CSG_ARENA
+#define EUCL_CSG_ARENA 256
+#endif
+constexpr int CSG_ARENA = EUCL_CSG_ARENA;     // compact hits per thread (scene_create validates programs against it)
 constexpr int CSG_LIST_STACK = 16; // nesting depth of pending child lists
 constexpr int CHAIN_ROOT_CAP = 32; // hits of a chain that is an entity's whole shape (<= 16 leaves)
 

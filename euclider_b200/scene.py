@@ -208,6 +208,12 @@ class Environment:
         assert len(rgba8) == width * height * 4
         check(lib().eucl_parsed_set_texture(self._parsed, slot, width, height, rgba8))
 
+    def memory(self, device: int = 0) -> dict:
+        """Device memory this environment's scene holds for frames: node arena, index lists, node capacity."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().eucl_scene_memory(self._device_scene(device), C.byref(a), C.byref(b), C.byref(c)))
+        return {"arena_bytes": a.value, "list_bytes": b.value, "node_capacity": c.value}
+
     def set_stream(self, cuda_stream: int, device: int = 0) -> None:
         """Runs this environment's kernels on `cuda_stream` (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(lib().eucl_scene_set_stream(self._device_scene(device), C.c_void_p(cuda_stream)))

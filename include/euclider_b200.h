@@ -297,6 +297,10 @@ typedef enum EuclPrecision { EUCL_PRECISION_F64 = 0, EUCL_PRECISION_F32 = 1 } Eu
 int eucl_scene_create_precision(const EuclFlatScene* flat, int device, int precision, EuclScene** out);
 void eucl_scene_destroy(EuclScene* scene);
 
+/* Device memory the scene holds for its frames right now: the node arena (rays, hits, node records, colours of every
+ * ray-tree node of a chunk), the index lists (shade bins and reach-key groups, one level each) and the node capacity. */
+int eucl_scene_memory(const EuclScene* scene, uint64_t* arena_bytes, uint64_t* list_bytes, uint64_t* node_capacity);
+
 /* Run this scene's kernels on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
  * stream) instead of the scene's own; NULL restores the private stream. */
 int eucl_scene_set_stream(EuclScene* scene, void* cuda_stream);

@@ -126,6 +126,14 @@ def test_full_size_rows_match_the_oracle(built_lib, oracle):
         assert np.array_equal(img.data[r0:r0 + 1], rgb) and np.array_equal(img.hit_ids[r0:r0 + 1], hit)
     again = env.render((w, h))
     assert np.array_equal(again.data, img.data)  # idempotent
+    # device memory of the whole-frame arena: 172 B per ray-tree node (ray, hit, node record, colour) plus index lists that
+    # hold one level each; the second frame has given back what the learning frame over-allocated
+    mem = env.memory()
+    assert img.stats["retries"] >= 1 and again.stats["retries"] == 0
+    assert mem["node_capacity"] >= img.stats["nodes"] and mem["node_capacity"] <= 1.1 * img.stats["nodes"]
+    assert mem["arena_bytes"] + mem["list_bytes"] < 11 * 2**30
+    print(f"3d_room 4K arena: {mem['arena_bytes'] / 2**30:.2f} GiB nodes + {mem['list_bytes'] / 2**30:.2f} GiB lists, "
+          f"{mem['node_capacity']} nodes for {img.stats['nodes']} used")
     env.pipeline = eb.EUCL_PIPELINE_MEGAKERNEL
     mega = env.render((w, h))
     assert np.array_equal(mega.data, img.data) and mega.stats["level_counts"] == img.stats["level_counts"]
