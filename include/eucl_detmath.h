@@ -12,6 +12,19 @@
  * below 1 ulp.  tests/test_detmath.py checks them against glibc.
  *
  * Usable from C++ and CUDA (all functions are EUCL_HD inline).
+ *
+ * The algorithms, argument reductions and coefficient tables of det_acos, det_asin, det_sin, det_cos, det_atan and
+ * det_atan2 are those of fdlibm (e_acos.c, e_asin.c, k_sin.c, k_cos.c, e_rem_pio2.c, s_atan.c, e_atan2.c), which is
+ * distributed under the following notice:
+ *
+ * ====================================================
+ * Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+ *
+ * Developed at SunSoft, a Sun Microsystems, Inc. business.
+ * Permission to use, copy, modify, and distribute this
+ * software is freely granted, provided that this notice
+ * is preserved.
+ * ====================================================
  */
 #ifndef EUCL_DETMATH_H
 #define EUCL_DETMATH_H

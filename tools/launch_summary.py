@@ -4,7 +4,7 @@
 
     python tools/launch_summary.py list.csv [--warmup 3] [--steps 2]
 
-A chunk sequence starts at k_camera_entity; sequences whose k_final ran for real (> 20 us, i.e. not an
+A chunk sequence starts at k_camera_entity (round 1) or k_raygen (round 2); sequences whose k_final ran for real (> 20 us, i.e. not an
 overflowed attempt that returned early) are complete; the frame's chunk count is read from the data."""
 import argparse
 import csv
@@ -28,11 +28,13 @@ for r in rows:
         unit = r[hdr.index("Metric Unit")]
         ns = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
         launches.append((m.group(1) if m else name[:40], ns))
-seqs, cur = [], None
+seqs, cur, prev = [], None, ""
 for name, ns in launches:
-    if name.startswith("k_camera_entity"):
+    # round 1 lists: a chunk starts at k_camera_entity; round 2: at k_raygen (the camera lookup moved into it)
+    if name.startswith("k_camera_entity") or (name.startswith("k_raygen") and not prev.startswith("k_camera_entity")):
         cur = []
         seqs.append(cur)
+    prev = name
     if cur is not None and name.startswith("k_"):
         cur.append((name, ns))
 complete = [s for s in seqs if any(n.startswith("k_final") and ns > 20e3 for n, ns in s)]
