@@ -723,10 +723,25 @@ int eucl_scene_create_precision(const EuclFlatScene* flat, int device, int preci
     // macro CSG programs replace the binary node list on the device
     MacroBuilder mb{*flat, {}};
     std::vector<EuclEntity> dev_entities((size_t)flat->n_entities);
+    // Complement(VoidShape, X) -- "everything but X": a room described by its interior (4d_room's walls).  VoidShape has no
+    // hits, so ComplementIterator only ever takes its `b`-only branch: every hit of X in order, normal negated, kept because
+    // VoidShape contains every point (shape.rs:394-408); is_point_inside is `true && !X` (shape.rs:596).  The device program of
+    // such an entity is X's program and the entity carries ENT_NEGATED: hits flip their normal flag, membership is inverted,
+    // and X's bound still bounds the hits (not the points the entity contains).  With X a chain of half-spaces the entity
+    // becomes a root plane chain: first-item shortcut, light intersect kernel.
+    std::vector<char> negated((size_t)std::max(flat->n_entities, 1), 0);
     for (int e = 0; e < flat->n_entities; ++e) {
         EuclEntity de = flat->entities[e];
         de.node_first = (int)mb.out.size();
-        mb.emit(flat->entities[e].node_root);
+        const int root = flat->entities[e].node_root;
+        const EuclNode& rn = flat->nodes[root];
+        if (rn.op == EUCL_CSG_COMPLEMENT && flat->nodes[mb.child_a(root)].op == EUCL_CSG_LEAF &&
+            flat->prims[flat->nodes[mb.child_a(root)].prim].kind == EUCL_PRIM_VOID && env_int("EUCL_NEGATED_ROOMS", 1)) {
+            negated[(size_t)e] = 1;
+            mb.emit(mb.child_b(root));
+        } else {
+            mb.emit(root);
+        }
         de.node_root = (int)mb.out.size() - 1;
         int peak = 0, depth = 0;
         if (!mb.fits(de.node_first, de.node_root, &peak, &depth))
@@ -745,7 +760,8 @@ int eucl_scene_create_precision(const EuclFlatScene* flat, int device, int preci
     h.off_bounds = w.put(bounds.data(), bounds.size());
     for (int e = 0; e < flat->n_entities && h.n_cull < 4; ++e) { // entities worth a reach-key bit
         const EuclEntity& de = dev_entities[(size_t)e];
-        if (de.surface >= 0 && mb.out[(size_t)de.node_root].kind != M_PRIM && bounds[(size_t)de.node_root].r2 >= 0.0)
+        // (not the negated ones: a room is reached by every ray inside it)
+        if (de.surface >= 0 && !negated[(size_t)e] && mb.out[(size_t)de.node_root].kind != M_PRIM && bounds[(size_t)de.node_root].r2 >= 0.0)
             h.cull_root[h.n_cull++] = de.node_root;
     }
     s->n_cull = h.n_cull;
@@ -755,9 +771,10 @@ int eucl_scene_create_precision(const EuclFlatScene* flat, int device, int preci
     bool light_capable = true;
     for (int e = 0; e < flat->n_entities; ++e) {
         const EuclEntity& de = dev_entities[(size_t)e];
+        if (negated[(size_t)e]) ent_flags[(size_t)e] = ENT_NEGATED; // material_at needs it for entities without a surface too
         if (de.surface < 0) continue;
         const MNode& root = mb.out[(size_t)de.node_root];
-        int fl = ENT_SURFACED;
+        int fl = ENT_SURFACED | ent_flags[(size_t)e];
         if (root.kind == M_PRIM) fl |= ENT_PRIM;
         else if (root.kind == M_CHAIN && de.node_first == de.node_root && (root.b & 0x4000) && (root.b & 0x3fff) <= kPlaneChainMax) fl |= ENT_ROOT_PLANES;
         for (int k = 0; k < h.n_cull; ++k)

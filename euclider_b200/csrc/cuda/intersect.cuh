@@ -181,6 +181,10 @@ template <int D>
 __device__ __noinline__ int material_at(const SceneView& sv, EUCL_VARG(Vec<D>) p) {
     for (int e = 0; e < sv.n_entities; ++e) {
         const int root = sv.entities()[e].node_root;
+        if (sv.ent_flags()[e] & ENT_NEGATED) { // Complement(VoidShape, X): true && !X (shape.rs:596); X's bound says nothing here
+            if (!node_inside<D>(sv, root, p)) return e;
+            continue;
+        }
         // a point outside the (inflated) bounding sphere of the shape cannot be inside it; NaN -> not skipped
         const Bound& bnd = sv.bounds()[root];
         if (R(bnd.r2) >= R(0.0)) {
@@ -604,6 +608,7 @@ __device__ __forceinline__ ClosestHit closest_hit(const SceneView& sv, const Vec
         } else { // one call site: the evaluator (and the chain code inside it) exists once in the kernel
             found = csg_first<D>(sv, ent.node_first, ent.node_root, o, d, ts, ts_stride, h);
         }
+        if (sv.ent_flags()[e] & ENT_NEGATED) h.flags ^= 2; // the `b`-only branch of ComplementIterator negates the normal
         if (found && (best.entity < 0 || best.t > h.t)) best = ClosestHit{e, h.prim, h.flags, h.t};
     }
     return best;
@@ -633,7 +638,7 @@ __device__ __forceinline__ ClosestHit closest_hit_light(const SceneView& sv, con
             t0 = ts[idx * ts_stride];
             prim = root.a + idx;
         }
-        if (found && (best.entity < 0 || best.t > t0)) best = ClosestHit{e, prim, 0, t0};
+        if (found && (best.entity < 0 || best.t > t0)) best = ClosestHit{e, prim, (flags & ENT_NEGATED) ? 2 : 0, t0};
     }
     return best;
 }

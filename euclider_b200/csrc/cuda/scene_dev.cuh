@@ -60,7 +60,8 @@ enum EntFlags : int32_t {
     ENT_SURFACED = 1,   // takes part in trace_closest
     ENT_PRIM = 2,       // the shape is one primitive
     ENT_ROOT_PLANES = 4, // the shape is one chain of <= kPlaneChainMax half-spaces
-    ENT_CULL_ROOT = 8   // owns a reach-key bit: rays with key 0 cannot hit it
+    ENT_CULL_ROOT = 8,  // owns a reach-key bit: rays with key 0 cannot hit it
+    ENT_NEGATED = 16    // Complement(VoidShape, X) lowered to X: hits flip their normal, membership is inverted
 };
 static_assert(sizeof(SceneHeader) % 16 == 0, "header must keep 16-byte alignment");
 
