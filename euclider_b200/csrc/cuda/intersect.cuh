@@ -291,7 +291,7 @@ __device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const real v = dot(nrm, p[g]) + c;
-            const bool in = !isnan(v) && ((__double2hiint(v) < 0) == s_neg);
+            const bool in = !isnan(v) && (sign_negative(v) == s_neg);
             rows[g] |= (in ? 1u : 0u) << j;
         }
     }
@@ -314,6 +314,9 @@ __device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N
 //     dynamically.
 // The list is a packed array of 4-bit leaf indices.  Returns the list length.
 constexpr int kPlaneChainMax = 8;
+#ifndef EUCL_LIST_SHORTCUT_MIN_N
+#define EUCL_LIST_SHORTCUT_MIN_N 0
+#endif
 template <int D>
 __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, int N, const Vec<D>& o, const Vec<D>& d,
                                            bool first_only, real* ts, int ts_stride, unsigned long long& list_out) {
@@ -330,15 +333,18 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         if (!(t < R(0.0))) exists |= 1u << i; // NaN and +inf pass
     }
     const bool want_in = op == EUCL_CSG_INTERSECTION;
-    if (first_only) {
-        // Shortcut for an entity's whole shape (only the first item of the stream is asked for, mod.rs:110-112).  Let m be
-        // the existing hit whose distance is STRICTLY smaller than every other existing one (no NaN anywhere).  If m
-        // passes the membership test against every other leaf (outside all of them for a Union, inside all for an
-        // Intersection), m is the first item of the final list: it enters the fold as `b` at its own step, where it is
-        // closer than every item of the list so far and is tested against the fold of the earlier leaves; at every later
-        // step it is the head of `a`, closer than the new `b`, and is tested against that one leaf.  Each of these tests
-        // is one of the N - 1 evaluated here, so m is emitted first every time.  (Rays inside a room or a box: always.)
-        // Anything else -- ties, NaN, a rejected m -- takes the general evaluation below.
+    {
+        // Shortcut.  Let m be the existing hit whose distance is STRICTLY smaller than every other existing one (no NaN
+        // anywhere), and let it pass the membership test against every other leaf (outside all of them for a Union, inside
+        // all for an Intersection).  Then m is the FIRST item of the folded list: it enters the fold as `b` at its own step,
+        // where it is closer than every item of the list so far and is tested against the fold of the earlier leaves; at
+        // every later step it is the head of `a`, closer than the new `b`, and is tested against that one leaf.  Each of
+        // these tests is one of the N - 1 evaluated here, so m is emitted first every time.  An entity's whole shape only
+        // ever yields its first item (mod.rs:110-112): done.  Inside a CSG program the whole list is needed; every item
+        // of the folded list has passed the test against ALL other leaves, so if every OTHER existing hit fails the test
+        // against leaf m alone, the list is exactly [m].  That is the case of a ray that starts inside a box (or outside
+        // every member of a union): one row and one column of the membership table instead of all of it, no replay.
+        // Anything else -- ties, NaN, a rejected m, another surviving candidate -- takes the general evaluation below.
         int m = -1;
         real tm = R(0.0);
         bool clean = true;
@@ -352,7 +358,7 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
                 tm = t;
             }
         }
-        if (m < 0) {
+        if (m < 0) { // no leaf is hit at all
             list_out = 0ull;
             return 0;
         }
@@ -360,15 +366,33 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
             const Vec<D> pm = d * tm + o;
             bool ok = true;
 #pragma unroll 1
-            for (int j = 0; j < N; ++j) {
+            for (int j = 0; j < N && ok; ++j) {
+                if (j == m) continue;
                 const double* r = rec + j * kPlaneStride;
                 Vec<D> nrm;
 #pragma unroll
                 for (int k = 0; k < D; ++k) nrm[k] = R(r[k]);
                 const real v = dot(nrm, pm) + R(r[4]);
-                const bool in = !isnan(v) && ((__double2hiint(v) < 0) == (r[5] < R(0.0)));
-                const bool tie = j != m && ((exists >> j) & 1u) && !(tm < ts[j * ts_stride]);
-                if (j != m && (in != want_in || tie)) ok = false;
+                const bool in = !isnan(v) && (sign_negative(v) == (r[5] < 0.0));
+                const bool tie = ((exists >> j) & 1u) && !(tm < ts[j * ts_stride]);
+                ok = in == want_in && !tie;
+            }
+            if (ok && !first_only && N < EUCL_LIST_SHORTCUT_MIN_N) ok = false; // small chains: the full table is cheap enough
+            if (ok && !first_only) { // column m: every other existing hit against leaf m
+                const double* r = rec + m * kPlaneStride;
+                Vec<D> nrm;
+#pragma unroll
+                for (int k = 0; k < D; ++k) nrm[k] = R(r[k]);
+                const real c = R(r[4]);
+                const bool s_neg = r[5] < 0.0;
+#pragma unroll 1
+                for (int i = 0; i < N && ok; ++i) {
+                    if (i == m || !((exists >> i) & 1u)) continue;
+                    const Vec<D> pi = d * ts[i * ts_stride] + o;
+                    const real v = dot(nrm, pi) + c;
+                    const bool in = !isnan(v) && (sign_negative(v) == s_neg);
+                    ok = in != want_in; // rejected by leaf m: cannot be in the folded list
+                }
             }
             if (ok) {
                 list_out = (unsigned long long)m;
