@@ -10,7 +10,7 @@ def _vec(d, xs, kind):
     return {f"{kind}{d}::new": [float(v) for v in xs[:d]]}
 
 
-def random_scene(seed: int, dim: int) -> str:
+def random_scene(seed: int, dim: int, rooms: bool = True) -> str:
     rng = np.random.default_rng(seed)
     d = dim
     P = lambda xs: _vec(d, xs, "Point")
@@ -87,6 +87,24 @@ def random_scene(seed: int, dim: int) -> str:
         return {f"Vacuum{d}::new": []}
 
     entities = [{f"Entity{d}Impl::new": [shape(int(rng.integers(1, 4))), material(), surface()]} for _ in range(int(rng.integers(2, 7)))]
+    if rooms:
+        # every third scene is enclosed by a room described by its interior, Complement(VoidShape, X), like 4d_room's walls:
+        # X a big box (a chain of half-spaces), a sphere, or a small CSG program around the camera
+        rng2 = np.random.default_rng(seed + 7_000_000)
+        if rng2.random() < 1.0 / 3.0:
+            centre = np.concatenate([[6.0], rng2.uniform(-1, 1, 3)])
+            kind = rng2.integers(0, 3)
+            if kind == 0:
+                dims = rng2.uniform(30.0, 44.0, 4)
+                x = {"HalfSpace3::cuboid": [P(centre), V(dims)]} if d == 3 else {"HalfSpace4::hypercuboid": [P(centre), V(dims)]}
+            elif kind == 1:
+                x = {f"Sphere{d}::new": [P(centre), float(rng2.uniform(18.0, 26.0))]}
+            else:
+                x = {f"ComposableShape{d}::of": [[{f"Sphere{d}::new": [P(centre), 24.0]},
+                                                 {f"Sphere{d}::new": [P(centre + np.array([9.0, 0, 0, 0])), 24.0]}],
+                                                {"SetOperation": ["Intersection"]}]}
+            room = {f"ComposableShape{d}::of": [[{f"VoidShape{d}": []}, x], {"SetOperation": ["Complement"]}]}
+            entities.append({f"Entity{d}Impl::new": [room, {f"Vacuum{d}::new": []}, surface()]})
     entities.append({f"Void{d}::new_with_vacuum": []})
     uv = {"uv_sphere_3": [{"Point3::new": [0, 0, 0]}]}
     if d == 4:

@@ -91,3 +91,30 @@ def test_one_environment_serves_both_precisions(built_lib, oracle):
     c = env.render((96, 54))
     assert np.array_equal(a.data, c.data)
     assert np.array_equal(b.data, oracle.render(env, 96, 54, variant="f32")[0])
+
+
+@pytest.mark.parametrize("dim", [3, 4])
+def test_f32_random_scenes_bit_exact(built_lib, oracle, dim):
+    """Random nested-CSG scenes (tests/random_scenes.py) in f32: the device CSG evaluator, plane-chain shortcuts, bound
+    culling with the wider f32 inflation and negated rooms against the f32 oracle."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    from random_scenes import random_scene
+
+    checked = 0
+    for seed in range(2000, 2016):
+        env = eb.Parser.default(resource_root=ROOT).parse(random_scene(seed, dim))
+        env.precision = "f32"
+        try:
+            img = env.render((96, 54), time=0.25, want_hit_ids=True)
+        except eb.EuclError as err:  # a program larger than the device evaluator's arena is refused, not mis-rendered
+            assert err.status == -21
+            continue
+        rgb, hit, st = oracle.render(env, 96, 54, time=0.25, variant="f32")
+        if st["csg_runaway"]:
+            continue
+        assert np.array_equal(img.hit_ids, hit), f"hit ids differ, seed {seed} dim {dim}"
+        assert img.stats["level_counts"] == st["level_counts"], f"level counts differ, seed {seed} dim {dim}"
+        assert np.array_equal(img.data, rgb), f"pixels differ, seed {seed} dim {dim}"
+        checked += 1
+    assert checked >= 10
