@@ -314,9 +314,6 @@ __device__ __forceinline__ void plane_rows(const double* __restrict__ rec, int N
 //     dynamically.
 // The list is a packed array of 4-bit leaf indices.  Returns the list length.
 constexpr int kPlaneChainMax = 8;
-#ifndef EUCL_LIST_SHORTCUT_MIN_N
-#define EUCL_LIST_SHORTCUT_MIN_N 0
-#endif
 template <int D>
 __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, int N, const Vec<D>& o, const Vec<D>& d,
                                            bool first_only, real* ts, int ts_stride, unsigned long long& list_out) {
@@ -333,7 +330,9 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         if (!(t < R(0.0))) exists |= 1u << i; // NaN and +inf pass
     }
     const bool want_in = op == EUCL_CSG_INTERSECTION;
-    {
+    // (whole lists only in 4-D, where a hypercuboid's table is 8 x 7 tests: with 3-D boxes (6 x 5) the shortcut paid for itself
+    // on 3d_hallways but cost 3d_room 0.3 ms of code shape in its heavy intersect kernel; measured, profiles/README.md)
+    if (first_only || D >= 4) {
         // Shortcut.  Let m be the existing hit whose distance is STRICTLY smaller than every other existing one (no NaN
         // anywhere), and let it pass the membership test against every other leaf (outside all of them for a Union, inside
         // all for an Intersection).  Then m is the FIRST item of the folded list: it enters the fold as `b` at its own step,
@@ -366,18 +365,16 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
             const Vec<D> pm = d * tm + o;
             bool ok = true;
 #pragma unroll 1
-            for (int j = 0; j < N && ok; ++j) {
-                if (j == m) continue;
+            for (int j = 0; j < N; ++j) { // no early exit: the loop stays branch-free (the hot callers pass all N - 1 tests)
                 const double* r = rec + j * kPlaneStride;
                 Vec<D> nrm;
 #pragma unroll
                 for (int k = 0; k < D; ++k) nrm[k] = R(r[k]);
                 const real v = dot(nrm, pm) + R(r[4]);
                 const bool in = !isnan(v) && (sign_negative(v) == (r[5] < 0.0));
-                const bool tie = ((exists >> j) & 1u) && !(tm < ts[j * ts_stride]);
-                ok = in == want_in && !tie;
+                const bool tie = j != m && ((exists >> j) & 1u) && !(tm < ts[j * ts_stride]);
+                if (j != m && (in != want_in || tie)) ok = false;
             }
-            if (ok && !first_only && N < EUCL_LIST_SHORTCUT_MIN_N) ok = false; // small chains: the full table is cheap enough
             if (ok && !first_only) { // column m: every other existing hit against leaf m
                 const double* r = rec + m * kPlaneStride;
                 Vec<D> nrm;
