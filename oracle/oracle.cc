@@ -12,10 +12,17 @@
 //
 // PARITY PINNING: the reference cannot be compiled here (no rustc/cargo, 20+ crates absent), so
 // this oracle is pinned by (1) the reference's own known-answer tests for this path
-// (shape.rs:1048-1148, util.rs:947-969,1007-1037; see tests/test_oracle_kats.py) and (2) code
-// reading.  Behaviour that lives in un-vendored crates (palette 0.2.1, noise 0.4.1, nalgebra
-// 0.8.2, json 0.11.13, meval 0.1.0, image 0.18) is "parity unpinned"; every such assumption is
-// listed in oracle/ASSUMPTIONS.md.
+// (shape.rs:1048-1148, util.rs:947-969,1007-1037; see tests/test_oracle_kats.py), (2) restatements
+// of the PUBLISHED definitions of the third-party arithmetic written independently of this file
+// (W3C / SVG compositing equations for palette's 17 blends, colorsys for HSV, the Fresnel equations in
+// sine / tangent form, exact integer arithmetic for json's number conversion:
+// tests/test_independent_pins.py) and (3) code reading.  What remains "parity unpinned" -- noise 0.4.1's
+// gradient table, nalgebra 0.8.2's operation order, image 0.18's decoders, meval's grammar -- is listed
+// with its alternatives in oracle/ASSUMPTIONS.md.
+//
+// Builds (oracle/Makefile): liboracle.so (glibc libm), liboracle_det.so (the deterministic libm the CUDA
+// path uses: bit-comparable), liboracle_f32.so (-DORACLE_F32: the reference's `low_precision` feature,
+// `type F = f32`, src/main.rs:46-49), liboracle_count.so (operation counters).
 //
 // Citations are relative to /root/reference/src/.
 #include <atomic>
