@@ -330,8 +330,9 @@ __device__ __forceinline__ int plane_chain(const SceneView& sv, int op, int p0, 
         if (!(t < R(0.0))) exists |= 1u << i; // NaN and +inf pass
     }
     const bool want_in = op == EUCL_CSG_INTERSECTION;
-    // (whole lists only in 4-D, where a hypercuboid's table is 8 x 7 tests: with 3-D boxes (6 x 5) the shortcut paid for itself
-    // on 3d_hallways but cost 3d_room 0.3 ms of code shape in its heavy intersect kernel; measured, profiles/README.md)
+    // (whole lists only in 4-D, where a hypercuboid's table is 8 x 7 tests.  For 3-D boxes (6 x 5) both ways of adding it were
+    // measured and lost on 3d_room's heavy intersect kernel: inlined 6.75 -> 6.94 ms of code shape, out of line 6.84 -> 7.12 ms
+    // of call overhead; profiles/README.md)
     if (first_only || D >= 4) {
         // Shortcut.  Let m be the existing hit whose distance is STRICTLY smaller than every other existing one (no NaN
         // anywhere), and let it pass the membership test against every other leaf (outside all of them for a Union, inside
