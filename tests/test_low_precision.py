@@ -118,3 +118,15 @@ def test_f32_random_scenes_bit_exact(built_lib, oracle, dim):
         assert np.array_equal(img.data, rgb), f"pixels differ, seed {seed} dim {dim}"
         checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("name,size", [("3d_room", (3840, 2160)), ("4d_room", (7680, 4320))])
+def test_f32_full_size_rows(built_lib, oracle, name, size):
+    """The two headline configs at full resolution in f32: sampled rows against the f32 oracle, bit for bit."""
+    env = load(name)
+    w, h = size
+    img = env.render((w, h), want_hit_ids=True)
+    for r0 in (0, h // 3, h // 2 - 1, h // 2, h - 1):
+        rgb, hit, _ = oracle.render(env, w, h, rows=(r0, r0 + 1), variant="f32")
+        assert np.array_equal(img.data[r0:r0 + 1], rgb) and np.array_equal(img.hit_ids[r0:r0 + 1], hit)
+    assert img.stats["pixels"] == w * h
