@@ -9,7 +9,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "error.h"
@@ -33,6 +37,11 @@ using namespace eucl;
 // the launcher of the scene's precision: namespace eucl holds the f64 build of kernels.cu, eucl_f32 the f32 build
 #define EUCL_PREC(fn) (s->real_bytes == 4 ? eucl_f32::fn : eucl::fn)
 
+// pipelines a rank's share of a frame is rendered as (render_split); EUCL_SPLIT overrides
+#ifndef EUCL_SPLIT_DEFAULT
+#define EUCL_SPLIT_DEFAULT 2
+#endif
+
 int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
     return v && *v ? std::atoi(v) : fallback;
@@ -54,6 +63,51 @@ struct DeviceBuffer {
         if (ptr) cudaFree(ptr);
         ptr = nullptr;
         bytes = 0;
+    }
+};
+
+// One helper thread per split scene: runs the second pipeline's host side (enqueue, stream synchronise, retry loop)
+// next to the caller's thread.  Kept alive between frames: waking it costs microseconds, creating it tens.
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = false, quit = false;
+    void start() {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || quit; });
+                if (quit) return;
+                lk.unlock();
+                job();
+                lk.lock();
+                has_job = false;
+                done = true;
+                cv.notify_all();
+            }
+        });
+    }
+    void run(std::function<void()> f) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f);
+        has_job = true;
+        done = false;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return done; });
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+            cv.notify_all();
+        }
+        th.join();
     }
 };
 
@@ -106,6 +160,13 @@ struct EuclScene {
     int list_capacity = 0;     // entries per index list (bins, reach keys): the largest LEVEL a chunk may have
     double list_factor = 1.0;  // ... in nodes per pixel (level 0 has exactly one; deeper levels are smaller in every shipped scene)
     int32_t* h_small = nullptr; // pinned mirror of the counters
+    // Further pipelines of a split frame (render_split): scenes of their own -- streams, arena, counters, graph --
+    // over the same uploaded blob and textures, each rendering every k-th band next to this one.
+    std::vector<EuclScene*> twins;
+    std::vector<Worker*> workers; // one host thread per twin
+    bool is_twin = false;
+    cudaEvent_t ev_split[3] = {nullptr, nullptr, nullptr}; // start (timed), fork, end (timed)
+    cudaEvent_t ev_done = nullptr;                         // twin: its part of the frame is on its stream
 };
 
 namespace {
@@ -585,10 +646,18 @@ int eucl_device_count(void) {
 void eucl_scene_destroy(EuclScene* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    for (Worker* w : s->workers) {
+        w->stop();
+        delete w;
+    }
+    for (EuclScene* t : s->twins) eucl_scene_destroy(t);
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto& e : s->ev_split)
+        if (e) cudaEventDestroy(e);
     for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
     for (auto a : s->arrays) cudaFreeArray(a);
-    if (s->d_blob) cudaFree(s->d_blob);
+    if (s->d_blob && !s->is_twin) cudaFree(s->d_blob);
     s->nodes.release();
     s->small.release();
     s->frame.release();
@@ -936,8 +1005,38 @@ Workspace carve(EuclScene* s, int dim, int cap, int list_cap) {
     return ws;
 }
 
+// ray grouping of the frame about to be rendered (see EuclScene::ray_bins_mode)
+void choose_grouping(EuclScene* s) {
+    const int forced = env_int("EUCL_BIN_RAYS", -1);
+    if (forced >= 0) s->ray_bins_mode = forced ? 1 : 0;
+    if (s->ray_bins_mode >= 0) s->ray_bins_now = s->ray_bins_mode == 1;
+    else s->ray_bins_now = s->tune_count[1] <= s->tune_count[0]; // undecided: alternate, "on" first
+}
+
+// Auto-tuning of the ray grouping (EuclScene::ray_bins_mode) from whole retry-free frames.
+void tune_grouping(EuclScene* s, const EuclStats& st, int pipeline) {
+    if (s->ray_bins_mode >= 0 || st.retries != 0 || st.pixels == 0 || pipeline != EUCL_PIPELINE_WAVEFRONT) return;
+    if (s->n_cull == 0) {
+        s->ray_bins_mode = 0;
+    } else if (s->warm_frames >= 1) { // never the scene's very first frame (allocations, cold caches)
+        if (s->tune_pixels != st.pixels) { // only frames of one size are comparable
+            s->tune_pixels = st.pixels;
+            s->tune_ms[0] = s->tune_ms[1] = 0.f;
+            s->tune_count[0] = s->tune_count[1] = 0;
+        }
+        // two frames per setting, alternating, the faster one of each counts: one slow frame (another process on
+        // the GPU, a clock ramp) must not decide; EuclStats.ray_grouping reports what a frame used
+        const int m = s->ray_bins_now ? 1 : 0;
+        s->tune_ms[m] = s->tune_count[m] == 0 ? st.ms_total : std::min(s->tune_ms[m], st.ms_total);
+        s->tune_count[m] += 1;
+        if (s->tune_count[0] >= 2 && s->tune_count[1] >= 2) s->ray_bins_mode = s->tune_ms[1] < s->tune_ms[0] ? 1 : 0;
+    }
+}
+
+// Renders this rank's rows of `o` (all of them, or -- sub_stride > 1 -- the bands that `o` names, which are every
+// sub_stride-th band of the caller's rank starting at sub_offset: render_split).
 int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* d_rgb, int32_t* d_hit,
-                EuclStats* stats) {
+                EuclStats* stats, int sub_stride = 1, int sub_offset = 0) {
     const int dim = s->dim;
     FrameParams fp;
     frame_params(*cam, *o, s->real_bytes, &fp);
@@ -945,12 +1044,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     const uint32_t my_rows = eucl_band_rows_for_rank(o);
     EuclStats st{};
     st.levels = cam->max_depth + 1;
-    {
-        const int forced = env_int("EUCL_BIN_RAYS", -1);
-        if (forced >= 0) s->ray_bins_mode = forced ? 1 : 0;
-        if (s->ray_bins_mode >= 0) s->ray_bins_now = s->ray_bins_mode == 1;
-        else s->ray_bins_now = s->tune_count[1] <= s->tune_count[0]; // undecided: alternate, "on" first
-    }
+    if (!s->is_twin) choose_grouping(s); // a twin renders with its leader's setting
     EUCL_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (my_rows > 0) {
         // chunking: whole local rows, about EUCL_CHUNK_PIXELS primaries per chunk.  Large chunks are faster (longer
@@ -988,6 +1082,8 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
             cp.band_rank = (int)o->band_rank;
             cp.band_world = o->band_world ? (int)o->band_world : 1;
             cp.compact_rows = o->compact_rows;
+            cp.sub_stride = sub_stride;
+            cp.sub_offset = sub_offset;
             for (;;) { // retry with a larger arena when a level overflowed, with a smaller chunk when the arena cannot grow
                 cp.n_rows = std::min<int>(rows_per_chunk, (int)my_rows - row0);
                 cp.n_pixels = cp.n_rows * width;
@@ -1140,10 +1236,14 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
                     s->graph_exec = nullptr;
                     cudaGraph_t graph = nullptr;
+                    // one capture at a time in the process (the pipelines of a split frame capture in the same frame)
+                    static std::mutex capture_mutex;
+                    std::unique_lock<std::mutex> capture_lock(capture_mutex);
                     EUCL_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
                     const uint32_t launches = enqueue();
                     cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
                     if (ce == cudaSuccess) ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+                    capture_lock.unlock();
                     if (graph) cudaGraphDestroy(graph);
                     if (ce != cudaSuccess) { // not capturable here (e.g. a caller's stream in a state that forbids it): launch directly
                         cudaGetLastError();
@@ -1241,25 +1341,140 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
             s->graph_key = s->seen_key = 0;
         }
     }
-    if (s->ray_bins_mode < 0 && st.retries == 0 && my_rows > 0 && o->pipeline == EUCL_PIPELINE_WAVEFRONT) {
-        if (s->n_cull == 0) {
-            s->ray_bins_mode = 0;
-        } else if (s->warm_frames >= 1) { // never the scene's very first frame (allocations, cold caches)
-            if (s->tune_pixels != st.pixels) { // only frames of one size are comparable
-                s->tune_pixels = st.pixels;
-                s->tune_ms[0] = s->tune_ms[1] = 0.f;
-                s->tune_count[0] = s->tune_count[1] = 0;
-            }
-            // two frames per setting, alternating, the faster one of each counts: one slow frame (another process on
-            // the GPU, a clock ramp) must not decide; EuclStats.ray_grouping reports what a frame used
-            const int m = s->ray_bins_now ? 1 : 0;
-            s->tune_ms[m] = s->tune_count[m] == 0 ? st.ms_total : std::min(s->tune_ms[m], st.ms_total);
-            s->tune_count[m] += 1;
-            if (s->tune_count[0] >= 2 && s->tune_count[1] >= 2) s->ray_bins_mode = s->tune_ms[1] < s->tune_ms[0] ? 1 : 0;
-        }
-    }
+    if (sub_stride <= 1) tune_grouping(s, st, o->pipeline); // (a split frame is judged as a whole: render_split)
     s->warm_frames++;
     st.ray_grouping = s->ray_bins_now && s->rorder.ptr != nullptr && o->pipeline == EUCL_PIPELINE_WAVEFRONT ? 1u : 0u;
+    if (stats) *stats = st;
+    return EUCL_OK;
+}
+
+// One more scene over the leader's uploaded blob and textures, with streams, events, counters and (later) an arena of its own.
+int add_twin(EuclScene* s) {
+    EuclScene* t = new EuclScene();
+    t->is_twin = true;
+    t->device = s->device;
+    t->dim = s->dim;
+    t->sm_count = s->sm_count;
+    t->blob_bytes = s->blob_bytes;
+    t->smem_bytes = s->smem_bytes;
+    t->smem_scene = s->smem_scene;
+    t->shade_light_mask = s->shade_light_mask;
+    t->shade_heavy_mask = s->shade_heavy_mask;
+    t->d_blob = s->d_blob;
+    t->n_cull = s->n_cull;
+    t->light_capable = s->light_capable;
+    t->n_entities = s->n_entities;
+    t->real_bytes = s->real_bytes;
+    cudaError_t e = cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking);
+    t->stream = t->own_stream;
+    if (e == cudaSuccess) e = cudaEventCreate(&t->ev[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&t->ev[1]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&t->h_small, sizeof(int32_t) * kSmallInts);
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k)
+        if (!s->ev_split[k]) e = cudaEventCreateWithFlags(&s->ev_split[k], k == 1 ? cudaEventDisableTiming : cudaEventDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        eucl_scene_destroy(t);
+        return fail(e == cudaErrorMemoryAllocation ? EUCL_ERR_OUT_OF_MEMORY : EUCL_ERR_CUDA, std::string("split pipeline: ") + cudaGetErrorString(e));
+    }
+    s->twins.push_back(t);
+    s->workers.push_back(new Worker());
+    s->workers.back()->start();
+    return EUCL_OK;
+}
+
+constexpr int kMaxSplit = 8;
+
+// Environment::render for this rank's rows, as ONE pipeline or as k side by side.
+//
+// A frame is ~50 dependent launches (raygen, then per level intersect and shade, then the resolves), and every one
+// of them ends with a tail in which the slowest rays of the level finish on a mostly idle GPU: about 0.55 ms per
+// 3d_room frame whatever its size (profiles/r2_band_scaling.txt) -- 3 % of a 4K frame on one GPU, 20 % of an
+// eighth of it.  Independent pipelines, each on every k-th 16-row band and on streams of its own, fill each other's
+// tails.  The picture cannot depend on it: pixels are independent (mod.rs:316-348).
+int render_split(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* d_rgb, int32_t* d_hit, EuclStats* stats) {
+    const uint32_t my_rows = eucl_band_rows_for_rank(o);
+    uint32_t world = o->band_world > 1 ? o->band_world : 1, rank = world > 1 ? o->band_rank : 0, band = o->band_rows;
+    if (band == 0) { // one band: the frame belongs to rank 0
+        world = 1;
+        rank = 0;
+        band = 16;
+    }
+    int k = std::min(kMaxSplit, env_int("EUCL_SPLIT", EUCL_SPLIT_DEFAULT));
+    k = (int)std::min<uint32_t>((uint32_t)std::max(k, 1), my_rows / band); // a band or more for every pipeline
+    if (o->pipeline != EUCL_PIPELINE_WAVEFRONT || (long long)my_rows * o->width < (long long)env_int("EUCL_SPLIT_MIN_PIXELS", 1 << 16)) k = 1;
+    if (k <= 1) return render_impl(s, cam, o, d_rgb, d_hit, stats);
+    while ((int)s->twins.size() < k - 1) {
+        int rc = add_twin(s);
+        if (rc != EUCL_OK) return rc;
+    }
+    choose_grouping(s);
+    EuclRenderOpts opts[kMaxSplit];
+    EuclStats part[kMaxSplit];
+    int rc[kMaxSplit];
+    std::string err[kMaxSplit];
+    for (int p = 0; p < k; ++p) {
+        opts[p] = *o;
+        opts[p].band_rows = band;
+        opts[p].band_world = (uint32_t)k * world;
+        opts[p].band_rank = rank + (uint32_t)p * world;
+        part[p] = EuclStats{};
+        rc[p] = EUCL_OK;
+    }
+    EUCL_CUDA(cudaEventRecord(s->ev_split[0], s->stream));
+    EUCL_CUDA(cudaEventRecord(s->ev_split[1], s->stream)); // the other pipelines start after whatever the caller's stream holds
+    // per-launch profiling and the debugging modes run the pipelines one after the other on the caller's thread
+    const bool serial = o->profile || env_int("EUCL_DEBUG_SYNC", 0) || env_int("EUCL_POISON", 0);
+    auto pipeline = [&](int p) {
+        EuclScene* t = s->twins[p - 1];
+        cudaSetDevice(t->device);
+        rc[p] = render_impl(t, cam, &opts[p], d_rgb, d_hit, &part[p], k, p);
+        if (rc[p] != EUCL_OK) err[p] = eucl_last_error();
+    };
+    for (int p = 1; p < k; ++p) {
+        EuclScene* t = s->twins[p - 1];
+        t->ray_bins_mode = s->ray_bins_mode;
+        t->ray_bins_now = s->ray_bins_now;
+        EUCL_CUDA(cudaStreamWaitEvent(t->stream, s->ev_split[1], 0));
+    }
+    // (no early return between here and the last wait(): the helper threads work on this frame's locals)
+    for (int p = 1; p < k && !serial; ++p) s->workers[p - 1]->run([&pipeline, p] { pipeline(p); });
+    rc[0] = render_impl(s, cam, &opts[0], d_rgb, d_hit, &part[0], k, 0);
+    for (int p = 1; p < k; ++p) {
+        if (serial) pipeline(p);
+        else s->workers[p - 1]->wait();
+    }
+    if (rc[0] != EUCL_OK) return rc[0];
+    for (int p = 1; p < k; ++p)
+        if (rc[p] != EUCL_OK) return fail(rc[p], err[p]);
+    for (int p = 1; p < k; ++p) { // the caller's stream continues after every pipeline
+        EuclScene* t = s->twins[p - 1];
+        EUCL_CUDA(cudaEventRecord(t->ev_done, t->stream));
+        EUCL_CUDA(cudaStreamWaitEvent(s->stream, t->ev_done, 0));
+    }
+    EUCL_CUDA(cudaEventRecord(s->ev_split[2], s->stream));
+    EUCL_CUDA(cudaEventSynchronize(s->ev_split[2]));
+    EuclStats st = part[0];
+    EUCL_CUDA(cudaEventElapsedTime(&st.ms_total, s->ev_split[0], s->ev_split[2]));
+    for (int p = 1; p < k; ++p) {
+        const EuclStats& b = part[p];
+        st.pixels += b.pixels;
+        st.segments += b.segments;
+        st.nodes += b.nodes;
+        for (uint32_t lv = 0; lv < EUCL_MAX_LEVELS; ++lv) st.level_counts[lv] += b.level_counts[lv];
+        st.launches += b.launches;
+        st.retries += b.retries;
+        st.graph_replays = std::min(st.graph_replays, b.graph_replays);
+        st.ms_raygen += b.ms_raygen;
+        st.ms_intersect += b.ms_intersect;
+        st.ms_shade += b.ms_shade;
+        st.ms_resolve += b.ms_resolve;
+    }
+    tune_grouping(s, st, o->pipeline);
     if (stats) *stats = st;
     return EUCL_OK;
 }
@@ -1286,7 +1501,7 @@ int eucl_render_device(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts
     if (st != EUCL_OK) return st;
     if (!d_out_rgb8) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_render_device: null output");
     EUCL_CUDA(cudaSetDevice(s->device));
-    return render_impl(s, cam, o, (uint8_t*)d_out_rgb8, o->want_hit_ids ? (int32_t*)d_out_hit_ids : nullptr, stats);
+    return render_split(s, cam, o, (uint8_t*)d_out_rgb8, o->want_hit_ids ? (int32_t*)d_out_hit_ids : nullptr, stats);
 }
 
 int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, uint8_t* out_rgb8, int32_t* out_hit_ids,
@@ -1308,7 +1523,7 @@ int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
     EuclRenderOpts opts = *o;
     opts.want_hit_ids = want_hit ? 1 : 0;
     if (scatter) opts.compact_rows = 1;
-    st = render_impl(s, cam, &opts, (uint8_t*)s->frame.ptr, want_hit ? (int32_t*)s->hit_ids.ptr : nullptr, stats);
+    st = render_split(s, cam, &opts, (uint8_t*)s->frame.ptr, want_hit ? (int32_t*)s->hit_ids.ptr : nullptr, stats);
     if (st != EUCL_OK) return st;
     if (!scatter) {
         EUCL_CUDA(cudaMemcpyAsync(out_rgb8, s->frame.ptr, pixels * 3, cudaMemcpyDeviceToHost, s->stream));
@@ -1336,9 +1551,15 @@ int eucl_render(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
 
 int eucl_scene_memory(const EuclScene* s, uint64_t* arena_bytes, uint64_t* list_bytes, uint64_t* node_capacity) {
     if (!s) return fail(EUCL_ERR_INVALID_ARGUMENT, "eucl_scene_memory: null scene");
-    if (arena_bytes) *arena_bytes = (uint64_t)s->nodes.bytes;
-    if (list_bytes) *list_bytes = (uint64_t)(s->order.bytes + s->rorder.bytes);
-    if (node_capacity) *node_capacity = (uint64_t)s->arena_capacity;
+    uint64_t arena = s->nodes.bytes, lists = s->order.bytes + s->rorder.bytes, cap = (uint64_t)s->arena_capacity;
+    for (const EuclScene* t : s->twins) { // a split scene holds one arena per pipeline
+        arena += t->nodes.bytes;
+        lists += t->order.bytes + t->rorder.bytes;
+        cap += (uint64_t)t->arena_capacity;
+    }
+    if (arena_bytes) *arena_bytes = arena;
+    if (list_bytes) *list_bytes = lists;
+    if (node_capacity) *node_capacity = cap;
     return EUCL_OK;
 }
 

@@ -122,6 +122,16 @@ __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
 // First queue position of this warp in the grid-stride walk of the queue kernels (CTA-contiguous).  Measured and not kept:
 // handing consecutive 32-entry chunks to different SMs so that the last, partly filled wave of a launch spreads over the
 // whole GPU -- no gain on a full 3d_room frame (15.79 vs 15.59 ms) nor on a 1/8-frame band (2.54 vs 2.50 ms).
+// CTAs of a launch that take part in walking `total` items: every thread gets EUCL_MIN_ITEMS items or more, so a small
+// level leaves SM slots to the kernels running beside it (the other build of the same stage, the other pipeline of a
+// split frame) instead of occupying the whole GPU with one or two items per thread; the rest of the grid exits at once.
+#ifndef EUCL_MIN_ITEMS
+#define EUCL_MIN_ITEMS 1
+#endif
+__device__ __forceinline__ int used_grid(int total) {
+    const int per_cta = (int)blockDim.x * EUCL_MIN_ITEMS;
+    return min((int)gridDim.x, (total + per_cta - 1) / per_cta);
+}
 __device__ __forceinline__ int warp_first_position() { return (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); }
 
 // Per-thread scratch column for plane_chain (kPlaneChainMax doubles per thread, element i of thread
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const uint8_t* __restrict__ b
                 store_res(ws, i, checkerboard(x, y));
                 ws.meta[i] = NodeMeta{R(0.0), -1, -1, 0u, NODE_LEAF | NODE_FINAL_RGB};
                 ws.ray_cur[i] = -1;
-                if (hit_ids_out) hit_ids_out[(size_t)(cp.compact_rows ? local_row : y) * fp.width + x] = -2;
+                if (hit_ids_out) hit_ids_out[(size_t)out_row_of_local(cp, local_row) * fp.width + x] = -2;
             }
             continue;
         }
@@ -407,11 +417,12 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
     }
     __syncthreads();
     const int total = s_total;
-    if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
+    const int grid_used = used_grid(total);
+    if (s_skip || (int)blockIdx.x >= grid_used) return;
     const SceneView& sv = stage_scene(blob);
     real* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
-    const int stride = gridDim.x * blockDim.x;
+    const int stride = grid_used * (int)blockDim.x;
     const int first = warp_first_position();
     int bin = 0; // the lists of a launch are walked front to back: the cursor only moves forward
     auto node_at = [&](int i) -> int {
@@ -524,12 +535,13 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
     }
     __syncthreads();
     const int total = s_total;
-    if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
+    const int grid_used = used_grid(total);
+    if (s_skip || (int)blockIdx.x >= grid_used) return;
     const SceneView& sv = stage_scene(blob);
     const int first = warp_first_position();
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
     const unsigned lane = threadIdx.x & 31u;
-    const int stride = gridDim.x * blockDim.x;
+    const int stride = grid_used * (int)blockDim.x;
     // node of position g; the bins of a launch are walked front to back, so the bin cursor only moves forward
     int bin = 0;
     auto node_at = [&](int g) -> int {
@@ -565,7 +577,7 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
             if (!last_level) ei = load_hit<D>(ws, node, n);
             if (level == 0 && hit_ids_out) {
                 const int local_row = cp.local_row0 + i / fp.width;
-                const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
+                const int orow = out_row_of_local(cp, local_row);
                 hit_ids_out[(size_t)orow * fp.width + i % fp.width] = ei.entity;
             }
             if (ei.entity < 0) {
@@ -686,7 +698,7 @@ __global__ void __launch_bounds__(256) k_final(FrameParams fp, ChunkParams cp, W
         const NodeMeta m = ws.meta[i];
         const Rgba c = node_color(ws, m, i);
         const int local_row = cp.local_row0 + i / fp.width;
-        const int orow = cp.compact_rows ? local_row : frame_row_of_local(cp, local_row);
+        const int orow = out_row_of_local(cp, local_row);
         final_rgb8(c, !(m.flags & NODE_FINAL_RGB), out_rgb8 + ((size_t)orow * fp.width + i % fp.width) * 3);
     }
 }
@@ -716,7 +728,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const uint8_t* __restrict
         const int local_row = cp.local_row0 + i / fp.width;
         const int x = i % fp.width;
         const int y = frame_row_of_local(cp, local_row);
-        const size_t opix = (size_t)(cp.compact_rows ? local_row : y) * fp.width + x;
+        const size_t opix = (size_t)out_row_of_local(cp, local_row) * fp.width + x;
         if (belongs_to < 0) {
             final_rgb8(checkerboard(x, y), false, out_rgb8 + opix * 3);
             if (hit_ids_out) hit_ids_out[opix] = -2;

@@ -31,6 +31,9 @@ struct ChunkParams {
     int32_t band_rows, band_rank, band_world;
     int32_t compact_rows; // 1: output row index = local row; 0: output row index = frame row
     int32_t n_pixels;     // n_rows * width
+    // one of `sub_stride` pipelines sharing a rank's bands (api_device.cu: render_split): band_rank / band_world above
+    // already name this pipeline's bands in the frame; in the rank's COMPACT buffer its band i is band i * stride + offset
+    int32_t sub_stride, sub_offset;
     int32_t _pad;
 };
 
@@ -38,6 +41,13 @@ __host__ __device__ inline int frame_row_of_local(const ChunkParams& c, int loca
     if (c.band_world <= 1) return local_row;
     int k = local_row / c.band_rows;
     return (k * c.band_world + c.band_rank) * c.band_rows + local_row % c.band_rows;
+}
+
+// row of the output buffer a local row is written to
+__host__ __device__ inline int out_row_of_local(const ChunkParams& c, int local_row) {
+    if (!c.compact_rows) return frame_row_of_local(c, local_row);
+    if (c.sub_stride <= 1) return local_row;
+    return ((local_row / c.band_rows) * c.sub_stride + c.sub_offset) * c.band_rows + local_row % c.band_rows;
 }
 
 // What the intersect kernel reports about a ray, one array-of-structures record of kHitDoubles doubles per node:
