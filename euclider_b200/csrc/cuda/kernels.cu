@@ -122,16 +122,9 @@ __device__ __forceinline__ Rgba load_res(const Workspace& ws, int node) {
 // First queue position of this warp in the grid-stride walk of the queue kernels (CTA-contiguous).  Measured and not kept:
 // handing consecutive 32-entry chunks to different SMs so that the last, partly filled wave of a launch spreads over the
 // whole GPU -- no gain on a full 3d_room frame (15.79 vs 15.59 ms) nor on a 1/8-frame band (2.54 vs 2.50 ms).
-// CTAs of a launch that take part in walking `total` items: every thread gets EUCL_MIN_ITEMS items or more, so a small
-// level leaves SM slots to the kernels running beside it (the other build of the same stage, the other pipeline of a
-// split frame) instead of occupying the whole GPU with one or two items per thread; the rest of the grid exits at once.
-#ifndef EUCL_MIN_ITEMS
-#define EUCL_MIN_ITEMS 1
-#endif
-__device__ __forceinline__ int used_grid(int total) {
-    const int per_cta = (int)blockDim.x * EUCL_MIN_ITEMS;
-    return min((int)gridDim.x, (total + per_cta - 1) / per_cta);
-}
+// Also measured and not kept: letting only ceil(total / (blockDim * m)) CTAs of a launch walk the level (m items or more per
+// thread, the rest of the grid exits at once) so that small levels leave SM slots to the kernels running beside them:
+// m = 2 / 4 / 8 -> an eighth of a 3d_room frame 2.26 / 2.53 / 3.60 ms against 2.29, full frames equal or slower.
 __device__ __forceinline__ int warp_first_position() { return (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); }
 
 // Per-thread scratch column for plane_chain (kPlaneChainMax doubles per thread, element i of thread
@@ -417,12 +410,11 @@ __global__ void __launch_bounds__(LIGHT ? kLightK2Block : kBlock, LIGHT ? EUCL_I
     }
     __syncthreads();
     const int total = s_total;
-    const int grid_used = used_grid(total);
-    if (s_skip || (int)blockIdx.x >= grid_used) return;
+    if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
     const SceneView& sv = stage_scene(blob);
     real* ts = plane_scratch(blob);
     const unsigned lane = threadIdx.x & 31u;
-    const int stride = grid_used * (int)blockDim.x;
+    const int stride = gridDim.x * blockDim.x;
     const int first = warp_first_position();
     int bin = 0; // the lists of a launch are walked front to back: the cursor only moves forward
     auto node_at = [&](int i) -> int {
@@ -535,13 +527,12 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
     }
     __syncthreads();
     const int total = s_total;
-    const int grid_used = used_grid(total);
-    if (s_skip || (int)blockIdx.x >= grid_used) return;
+    if (s_skip || (int)(blockIdx.x * blockDim.x) >= total) return;
     const SceneView& sv = stage_scene(blob);
     const int first = warp_first_position();
     const int next_off = last_level ? 0 : ws.level_off[level + 1];
     const unsigned lane = threadIdx.x & 31u;
-    const int stride = grid_used * (int)blockDim.x;
+    const int stride = gridDim.x * blockDim.x;
     // node of position g; the bins of a launch are walked front to back, so the bin cursor only moves forward
     int bin = 0;
     auto node_at = [&](int g) -> int {
