@@ -494,6 +494,10 @@ def main():
             "flops_per_segment": f_scene, "kernel": "k_intersect, light + heavy build, all levels of one frame (slowest rank)",
             "achieved": achieved, "frac": achieved / (peak * world) if achieved else None, "kernel_ms_per_frame": m["k_intersect_ms_max"],
             "family_ms": {k: m["prof"][k] for k in ("ms_raygen", "ms_intersect", "ms_shade", "ms_resolve", "ms_total")},
+            # the timed frames run two pipelines side by side (EUCL_SPLIT); the profile frame runs the same launches one after
+            # the other with an event after each, so its family times add up to more than ms_per_step and `frac` is the
+            # kernels' rate when timed alone, launch by launch
+            "kernel_share_of_profile_frame": m["prof"]["ms_intersect"] / max(1e-9, sum(m["prof"][k] for k in ("ms_raygen", "ms_intersect", "ms_shade", "ms_resolve"))),
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only

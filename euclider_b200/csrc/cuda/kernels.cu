@@ -614,13 +614,21 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
                 const unsigned lt = (1u << lane) - 1u;
                 ChildRay<D> child; // one child at a time: built, stored, forgotten
                 if (dec.t_emit) {
+#if EUCL_PAIR_CHILDREN
+                    tchild = next_off + slot + __popc(tmask & lt) + __popc(rmask & lt);
+#else
                     tchild = next_off + slot + __popc(tmask & lt);
+#endif
                     transmit_child<D, GLASS>(sv, d, cur, ei.entity, exiting, p, n, dec, child);
                     store_ray<D>(ws, tchild, child.o, child.d, child.cur);
                     if (RAY_BINS) tkey = reach_key<D>(sv, child.o, child.d);
                 }
                 if (dec.r_emit) {
+#if EUCL_PAIR_CHILDREN
+                    rchild = next_off + slot + __popc(tmask & lt) + __popc(rmask & lt) + (dec.t_emit ? 1 : 0);
+#else
                     rchild = next_off + slot + nt + __popc(rmask & lt);
+#endif
                     reflect_child<D>(d, cur, exiting, p, n, child);
                     store_ray<D>(ws, rchild, child.o, child.d, child.cur);
                     if (RAY_BINS) rkey = reach_key<D>(sv, child.o, child.d);

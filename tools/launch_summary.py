@@ -4,8 +4,10 @@
 
     python tools/launch_summary.py list.csv [--warmup 3] [--steps 2]
 
-A chunk sequence starts at k_camera_entity (round 1) or k_raygen (round 2); sequences whose k_final ran for real (> 20 us, i.e. not an
-overflowed attempt that returned early) are complete; the frame's chunk count is read from the data."""
+A frame attempt starts at a k_raygen (round 1: k_camera_entity) that follows as many k_final as there were k_raygen before it
+(the pipelines of a split frame interleave: two k_raygen, ..., two k_final); attempts whose k_final ran for real (> 20 us, i.e.
+not an overflowed attempt that returned early) are complete.  --chunks-per-frame N > 0 selects the older reading (a sequence per
+k_raygen, N sequences per frame) for the lists of round 1 and early round 2."""
 import argparse
 import csv
 import re
@@ -15,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("csv")
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--steps", type=int, default=2)
-ap.add_argument("--chunks-per-frame", type=int, default=2)
+ap.add_argument("--chunks-per-frame", type=int, default=0)
 args = ap.parse_args()
 rows = list(csv.reader(open(args.csv, errors="replace")))
 hdr = next(r for r in rows if "Kernel Name" in r)
@@ -29,16 +31,25 @@ for r in rows:
         ns = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
         launches.append((m.group(1) if m else name[:40], ns))
 seqs, cur, prev = [], None, ""
+open_raygens = 0
 for name, ns in launches:
-    # round 1 lists: a chunk starts at k_camera_entity; round 2: at k_raygen (the camera lookup moved into it)
-    if name.startswith("k_camera_entity") or (name.startswith("k_raygen") and not prev.startswith("k_camera_entity")):
+    if args.chunks_per_frame > 0:
+        # round 1 lists: a chunk starts at k_camera_entity; round 2: at k_raygen (the camera lookup moved into it)
+        start = name.startswith("k_camera_entity") or (name.startswith("k_raygen") and not prev.startswith("k_camera_entity"))
+    else:
+        start = name.startswith("k_raygen") and open_raygens == 0
+    if start:
         cur = []
         seqs.append(cur)
+    if name.startswith("k_raygen"):
+        open_raygens += 1
+    elif name.startswith("k_final"):
+        open_raygens = max(0, open_raygens - 1)
     prev = name
     if cur is not None and name.startswith("k_"):
         cur.append((name, ns))
 complete = [s for s in seqs if any(n.startswith("k_final") and ns > 20e3 for n, ns in s)]
-c = args.chunks_per_frame
+c = max(1, args.chunks_per_frame)
 timed = complete[args.warmup * c:(args.warmup + args.steps) * c]
 tot = OrderedDict()
 for s in timed:
