@@ -271,6 +271,27 @@ __device__ __forceinline__ void shade_hit(const SceneView& sv, real time_millis,
 __device__ __forceinline__ Rgba transmit_over(unsigned q, const Rgba& child) {
     return from_premultiplied(over_pre(into_premultiplied(new_u8(q)), into_premultiplied(new_u8(to_pixel4(child)))));
 }
+// The same with Rgba::new_u8's eight divisions by 255 read from a table of the 256 quotients (`unit[v] = v / 255`, filled by
+// fill_unit_table with that very division, so the values are the same bits): the resolve kernels are issue-bound, not
+// memory-bound, and an f64 division is ~30 instructions (profiles/README.md, resolve capture).
+__device__ __forceinline__ Rgba new_u8(unsigned q, const real* __restrict__ unit) {
+    return Rgba{unit[q & 255u], unit[(q >> 8) & 255u], unit[(q >> 16) & 255u], unit[q >> 24]};
+}
+// from_premultiplied with the three divisions skipped when alpha is exactly 1 (x / 1 is x: the usual case here, an opaque
+// child behind the surface); NaN channels stay NaN, which is all that is ever asked of them (channel_to_u8)
+__device__ __forceinline__ Rgba from_premultiplied_resolve(const Pre& p) {
+    const real a = clamp01(p.a);
+    if (a == R(1.0)) return Rgba{p.r, p.g, p.b, a};
+    return from_premultiplied(p);
+}
+__device__ __forceinline__ Rgba transmit_over(unsigned q, const Rgba& child, const real* __restrict__ unit) {
+    return from_premultiplied_resolve(over_pre(into_premultiplied(new_u8(q, unit)), into_premultiplied(new_u8(to_pixel4(child), unit))));
+}
+// 256-thread CTAs: one quotient per thread
+__device__ __forceinline__ void fill_unit_table(real* unit) {
+    for (unsigned v = threadIdx.x; v < 256u; v += blockDim.x) unit[v] = (real)v / R(255.0);
+    __syncthreads();
+}
 
 // trace_unknown tail (mod.rs:260-270) + to_pixel (mod.rs:342): composite over opaque white
 __device__ __forceinline__ void final_rgb8(const Rgba& fg, bool composite, uint8_t* out) {
@@ -589,7 +610,9 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
                 shaded = true;
             }
         }
-        // warp-aggregated append of the children to level + 1: one atomicAdd per warp
+        // warp-aggregated append of the children to level + 1: one atomicAdd per warp.  (Measured and not kept: adjacent
+        // slots for the two children of a node, so that the resolve reads them as one 64-byte piece: resolve 1.77 -> 1.77 ms,
+        // shade 7.60 -> 8.01.)
         const unsigned tmask = __ballot_sync(0xffffffffu, dec.t_emit), rmask = __ballot_sync(0xffffffffu, dec.r_emit);
         const int nt = __popc(tmask), n_children = nt + __popc(rmask);
         int slot = 0;
@@ -614,21 +637,13 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
                 const unsigned lt = (1u << lane) - 1u;
                 ChildRay<D> child; // one child at a time: built, stored, forgotten
                 if (dec.t_emit) {
-#if EUCL_PAIR_CHILDREN
-                    tchild = next_off + slot + __popc(tmask & lt) + __popc(rmask & lt);
-#else
                     tchild = next_off + slot + __popc(tmask & lt);
-#endif
                     transmit_child<D, GLASS>(sv, d, cur, ei.entity, exiting, p, n, dec, child);
                     store_ray<D>(ws, tchild, child.o, child.d, child.cur);
                     if (RAY_BINS) tkey = reach_key<D>(sv, child.o, child.d);
                 }
                 if (dec.r_emit) {
-#if EUCL_PAIR_CHILDREN
-                    rchild = next_off + slot + __popc(tmask & lt) + __popc(rmask & lt) + (dec.t_emit ? 1 : 0);
-#else
                     rchild = next_off + slot + nt + __popc(rmask & lt);
-#endif
                     reflect_child<D>(d, cur, exiting, p, n, child);
                     store_ray<D>(ws, rchild, child.o, child.d, child.cur);
                     if (RAY_BINS) rkey = reach_key<D>(sv, child.o, child.d);
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
 // Colour of a node from the (already final) colours of its children (surface.rs:104-114 transmitted, :150-161 combine).
 // Measured and not kept: resolving two levels per launch with the middle level's colours in registers (5 launches instead of
 // 10, a quarter less traffic, but a dependent chain of two gathers per thread): 3d_room 1.68 -> 2.03 ms, 4d_room 0.95 -> 1.06.
-__device__ __forceinline__ Rgba node_color(const Workspace& ws, const NodeMeta& m, int node) {
+__device__ __forceinline__ Rgba node_color(const Workspace& ws, const NodeMeta& m, int node, const real* __restrict__ unit) {
     if (m.flags & NODE_LEAF) return load_res(ws, node);
     bool have_t = false;
     Rgba t{R(0.0), R(0.0), R(0.0), R(0.0)};
@@ -667,7 +682,7 @@ __device__ __forceinline__ Rgba node_color(const Workspace& ws, const NodeMeta& 
         t = load_res(ws, node);
         have_t = true;
     } else if (m.tchild >= 0) {
-        t = transmit_over(m.q, load_res(ws, m.tchild));
+        t = transmit_over(m.q, load_res(ws, m.tchild), unit);
         have_t = true;
     }
     Rgba out = t;
@@ -680,22 +695,26 @@ __device__ __forceinline__ Rgba node_color(const Workspace& ws, const NodeMeta& 
 
 // K4: colour of the inner nodes of one level from the colours of level + 1.
 __global__ void __launch_bounds__(256) k_resolve(Workspace ws, int level) {
+    __shared__ real s_unit[256];
     if (*ws.overflow) return;
+    fill_unit_table(s_unit);
     const int off = ws.level_off[level], cnt = ws.count[level];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int node = off + i;
         const NodeMeta m = ws.meta[node];
         if (m.flags & NODE_LEAF) continue;
-        store_res(ws, node, node_color(ws, m, node));
+        store_res(ws, node, node_color(ws, m, node, s_unit));
     }
 }
 
 // K5: resolve level 0, composite over white, quantise and pack RGB8 rows (row 0 = bottom).
 __global__ void __launch_bounds__(256) k_final(FrameParams fp, ChunkParams cp, Workspace ws, uint8_t* __restrict__ out_rgb8) {
+    __shared__ real s_unit[256];
     if (*ws.overflow) return;
+    fill_unit_table(s_unit);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cp.n_pixels; i += gridDim.x * blockDim.x) {
         const NodeMeta m = ws.meta[i];
-        const Rgba c = node_color(ws, m, i);
+        const Rgba c = node_color(ws, m, i, s_unit);
         const int local_row = cp.local_row0 + i / fp.width;
         const int orow = out_row_of_local(cp, local_row);
         final_rgb8(c, !(m.flags & NODE_FINAL_RGB), out_rgb8 + ((size_t)orow * fp.width + i % fp.width) * 3);

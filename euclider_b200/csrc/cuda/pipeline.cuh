@@ -135,9 +135,6 @@ constexpr int kResidentThreads = 512;       // per SM at 128 registers per threa
 #ifndef EUCL_LIGHT_BLOCK
 #define EUCL_LIGHT_BLOCK 256
 #endif
-#ifndef EUCL_PAIR_CHILDREN
-#define EUCL_PAIR_CHILDREN 0 // 1: the two children of a node take adjacent slots of the next level
-#endif
 #ifndef EUCL_SHADE_LIGHT_MIN_BLOCKS
 #define EUCL_SHADE_LIGHT_MIN_BLOCKS 2 /* 3d_room 4K, shade ms per frame: 3 CTAs of 256 (80 registers, 370 B of spills) 8.50; 5 of 128 (96) 8.03; 4 of 128 / 2 of 256 (128 registers, no spills) 7.29 / 7.16 */
 #endif
