@@ -277,15 +277,8 @@ __device__ __forceinline__ Rgba transmit_over(unsigned q, const Rgba& child) {
 __device__ __forceinline__ Rgba new_u8(unsigned q, const real* __restrict__ unit) {
     return Rgba{unit[q & 255u], unit[(q >> 8) & 255u], unit[(q >> 16) & 255u], unit[q >> 24]};
 }
-// from_premultiplied with the three divisions skipped when alpha is exactly 1 (x / 1 is x: the usual case here, an opaque
-// child behind the surface); NaN channels stay NaN, which is all that is ever asked of them (channel_to_u8)
-__device__ __forceinline__ Rgba from_premultiplied_resolve(const Pre& p) {
-    const real a = clamp01(p.a);
-    if (a == R(1.0)) return Rgba{p.r, p.g, p.b, a};
-    return from_premultiplied(p);
-}
 __device__ __forceinline__ Rgba transmit_over(unsigned q, const Rgba& child, const real* __restrict__ unit) {
-    return from_premultiplied_resolve(over_pre(into_premultiplied(new_u8(q, unit)), into_premultiplied(new_u8(to_pixel4(child), unit))));
+    return from_premultiplied(over_pre(into_premultiplied(new_u8(q, unit)), into_premultiplied(new_u8(to_pixel4(child), unit))));
 }
 // 256-thread CTAs: one quotient per thread
 __device__ __forceinline__ void fill_unit_table(real* unit) {

@@ -40,6 +40,9 @@ __device__ __forceinline__ Pre into_premultiplied(const Rgba& c) {
 __device__ __forceinline__ bool is_normal(real a) { return isfinite(a) && fabs(a) >= kMinNormal; }
 __device__ __forceinline__ Rgba from_premultiplied(const Pre& p) {
     real a = clamp01(p.a);
+    // x / 1 is x: the three divisions (~30 instructions each in f64) are skipped for an opaque colour, the usual case.
+    // A NaN channel stays a NaN, which is all that is ever asked of it (channel_to_u8, comparisons).
+    if (a == R(1.0)) return Rgba{p.r, p.g, p.b, a};
     if (is_normal(a)) return Rgba{p.r / a, p.g / a, p.b / a, a};
     return Rgba{R(0.0), R(0.0), R(0.0), a};
 }
