@@ -666,7 +666,8 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
 
 // Colour of a node from the (already final) colours of its children (surface.rs:104-114 transmitted, :150-161 combine).
 // Measured and not kept: resolving two levels per launch with the middle level's colours in registers (5 launches instead of
-// 10, a quarter less traffic, but a dependent chain of two gathers per thread): 3d_room 1.68 -> 2.03 ms, 4d_room 0.95 -> 1.06.
+// 10, a quarter less traffic, but a dependent chain of two gathers per thread): 3d_room 1.68 -> 2.03 ms, 4d_room 0.95 -> 1.06;
+// two nodes per thread and iteration with both nodes' gathers issued before either is composed: 0.98 -> 1.04 ms.
 __device__ __forceinline__ Rgba node_color(const Workspace& ws, const NodeMeta& m, int node, const real* __restrict__ unit) {
     if (m.flags & NODE_LEAF) return load_res(ws, node);
     bool have_t = false;
