@@ -517,6 +517,7 @@ def main():
                                        + ("peer stores into GPU 0's frame (CUDA IPC over NVLink), frame-complete flag = "
                                           "stream-ordered all-reduce" if rig.peer else "NCCL gather to rank 0"))
                        if world > 1 else "single GPU",
+                       "pipelines_per_frame": int(os.environ.get("EUCL_SPLIT", "2")),  # concurrent pipelines per rank (render_split)
                        "l2": "node arena (GBs per chunk) is far larger than the 126 MB L2; no explicit flush"},
             "fps": 1e3 / m["ms_per_step"], "e2e": m["e2e"], "gpu_launches": m["launches"], "retries": m["retries"],
             "clocks": m["clocks"], "rank_device_ms": {"min": min(m["rank_ms"]), "max": max(m["rank_ms"]), "per_rank": m["rank_ms"]},

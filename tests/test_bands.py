@@ -72,3 +72,21 @@ def test_two_rank_gather_gloo(oracle):
     env = eb.load_reference_scene("3d_fresnel")
     whole = oracle.render(env, width, height)[0]
     assert np.array_equal(frame, whole)
+
+
+def test_sub_pipelines_partition_a_ranks_rows():
+    """render_split hands pipeline p of k the bands of rank `rank + p * world` in a world of `k * world`: together they
+    are exactly the rank's rows, for ragged heights too."""
+    lib = eb.lib()
+    for height in (1, 16, 31, 32, 67, 131, 2160):
+        for band in (4, 16):
+            for world in (1, 2, 3, 8):
+                for rank in range(world):
+                    whole = eb.EuclRenderOpts(width=4, height=height, band_rows=band, band_rank=rank, band_world=world)
+                    for k in (2, 3):
+                        parts = 0
+                        for p in range(k):
+                            sub = eb.EuclRenderOpts(width=4, height=height, band_rows=band, band_rank=rank + p * world,
+                                                    band_world=k * world)
+                            parts += lib.eucl_band_rows_for_rank(sub)
+                        assert parts == lib.eucl_band_rows_for_rank(whole), (height, band, world, rank, k)
