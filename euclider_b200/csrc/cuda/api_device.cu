@@ -1402,7 +1402,7 @@ int render_split(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, u
     if (band == 0) { // one band: the frame belongs to rank 0
         world = 1;
         rank = 0;
-        band = 16;
+        band = (uint32_t)std::max(1, env_int("EUCL_SPLIT_BAND_ROWS", 16));
     }
     int k = std::min(kMaxSplit, env_int("EUCL_SPLIT", EUCL_SPLIT_DEFAULT));
     k = (int)std::min<uint32_t>((uint32_t)std::max(k, 1), my_rows / band); // a band or more for every pipeline
