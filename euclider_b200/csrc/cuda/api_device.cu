@@ -1068,7 +1068,7 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                  s->sm_count * std::max(1, env_int("EUCL_LIGHT_K2_BLOCKS_PER_SM", kLightK2ResidentBlocks)), s->light_capable, s->n_cull,
                  // per-launch profiling and the debugging modes keep everything on one stream
                  (o->profile || env_int("EUCL_DEBUG_SYNC", 0) || !env_int("EUCL_CONCURRENT", 1)) ? nullptr : s->side_stream, s->ev_fork,
-                 s->ev_join};
+                 s->ev_join, s->sm_count * std::max(1, env_int("EUCL_BACKGROUND_BLOCKS_PER_SM", EUCL_BACKGROUND_MIN_BLOCKS))};
         const bool want_rorder = o->pipeline == EUCL_PIPELINE_WAVEFRONT && s->n_cull > 0 && env_int("EUCL_BIN_RAYS", 1);
         // shade-coherence bins: one node list per hit entity (+ miss), each able to hold a whole level
         const bool want_order = o->pipeline == EUCL_PIPELINE_WAVEFRONT && kBinsPerEntity * s->n_entities + 1 <= kMaxBins && env_int("EUCL_BIN_SHADE", 1);
@@ -1215,7 +1215,8 @@ int render_impl(EuclScene* s, const EuclCamera* cam, const EuclRenderOpts* o, ui
                     const unsigned long long nums[] = {l.smem_bytes, l.smem_scene, (unsigned long long)l.grid_max, (unsigned long long)l.grid_light,
                                                        (unsigned long long)l.grid_shade, (unsigned long long)l.grid_mem, l.shade_light_mask,
                                                        l.shade_heavy_mask, (unsigned long long)l.grid_light_k2,
-                                                       (unsigned long long)l.light_capable, (unsigned long long)l.n_cull};
+                                                       (unsigned long long)l.light_capable, (unsigned long long)l.n_cull,
+                                                       (unsigned long long)l.grid_background};
                     mix(ptrs, sizeof ptrs);
                     mix(nums, sizeof nums);
                 }

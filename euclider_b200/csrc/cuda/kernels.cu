@@ -664,6 +664,32 @@ __global__ void __launch_bounds__(GLASS ? kShadeBlock : kLightBlock, GLASS ? EUC
     }
 }
 
+// K3 of the LAST level: depth 0, `background.get_color(direction)` without intersecting (mod.rs:157,183).  A kernel of its
+// own because k_shade's register budget (128: the surface programs) would keep only 16 warps per SM resident for what is
+// a direction -> texture lookup per node (profiles/README.md: last-level capture).
+template <int D>
+__global__ void __launch_bounds__(256, EUCL_BACKGROUND_MIN_BLOCKS)
+    k_background(const uint8_t* __restrict__ blob, FrameParams fp, ChunkParams cp, Workspace ws, int level, int32_t* __restrict__ hit_ids_out) {
+    const int off = ws.level_off[level], cnt = ws.count[level];
+    __shared__ int s_skip; // decided once per block (see k_shade)
+    if (threadIdx.x == 0) s_skip = level > 0 && *ws.overflow != 0;
+    __syncthreads();
+    if (s_skip || (int)(blockIdx.x * blockDim.x) >= cnt) return;
+    const SceneView& sv = stage_scene(blob);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const int node = off + i;
+        if (ws.ray_cur[node] < 0) continue; // checkerboard pixels carry no ray
+        Vec<D> o, d;
+        load_ray<D>(ws, node, o, d);
+        if (level == 0 && hit_ids_out) { // max_depth 0: every primary ray goes to the background
+            const int local_row = cp.local_row0 + i / fp.width;
+            hit_ids_out[(size_t)out_row_of_local(cp, local_row) * fp.width + i % fp.width] = -1;
+        }
+        store_res(ws, node, mapped_color<D>(sv, sv.background, d));
+        ws.meta[node] = NodeMeta{R(0.0), -1, -1, 0u, NODE_LEAF};
+    }
+}
+
 // Colour of a node from the (already final) colours of its children (surface.rs:104-114 transmitted, :150-161 combine).
 // Measured and not kept: resolving two levels per launch with the middle level's colours in registers (5 launches instead of
 // 10, a quarter less traffic, but a dependent chain of two gathers per thread): 3d_room 1.68 -> 2.03 ms, 4d_room 0.95 -> 1.06;
@@ -1004,8 +1030,10 @@ int launch_shade(int dim, const Launch& l, const FrameParams& fp, const ChunkPar
     const bool last_level = level >= fp.max_depth;
     unsigned long long light = l.shade_light_mask, heavy = l.shade_heavy_mask;
     if (last_level) { // background lookups only
-        light = ~0ull;
-        heavy = 0ull;
+        const int grid = l.grid_background;
+        EUCL_DISPATCH_DIM(dim, (k_background<3><<<grid, 256, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)),
+                          (k_background<4><<<grid, 256, l.smem_scene, l.stream>>>(l.blob, fp, cp, ws, level, hit_ids_out)));
+        return 1;
     } else if (ws.n_bins <= 1) { // not binned: one kernel that can shade everything
         light = 0ull;
         heavy = ~0ull;
@@ -1094,6 +1122,8 @@ cudaError_t configure_kernels(size_t smem_bytes, size_t smem_scene) {
     EUCL_CONF((k_shade<4, true, false>), smem_scene, kLightResidentBlocks);
     EUCL_CONF((k_shade<3, false, false>), smem_scene, kLightResidentBlocks);
     EUCL_CONF((k_shade<4, false, false>), smem_scene, kLightResidentBlocks);
+    EUCL_CONF(k_background<3>, smem_scene, EUCL_BACKGROUND_MIN_BLOCKS);
+    EUCL_CONF(k_background<4>, smem_scene, EUCL_BACKGROUND_MIN_BLOCKS);
     EUCL_CONF(k_megakernel<3>, smem_bytes, heavy);
     EUCL_CONF(k_megakernel<4>, smem_bytes, heavy);
     EUCL_CONF(k_trace_path<3>, smem_bytes, 1);

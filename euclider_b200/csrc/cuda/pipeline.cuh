@@ -125,6 +125,7 @@ struct Launch {
     // concurrently (fork / join through the two events), so the tail of one overlaps the body of the other.
     cudaStream_t side;  // nullptr: launch one after the other on `stream`
     cudaEvent_t ev_fork, ev_join;
+    int grid_background; // blocks of the last level's kernel (256 threads each), one wave
 };
 
 #ifndef EUCL_BLOCK
@@ -134,6 +135,9 @@ constexpr int kBlock = EUCL_BLOCK;          // threads per CTA of the scene-walk
 constexpr int kResidentThreads = 512;       // per SM at 128 registers per thread (k_intersect, k_shade)
 #ifndef EUCL_LIGHT_BLOCK
 #define EUCL_LIGHT_BLOCK 256
+#endif
+#ifndef EUCL_BACKGROUND_MIN_BLOCKS
+#define EUCL_BACKGROUND_MIN_BLOCKS 3 /* resident 256-thread CTAs per SM of k_background */
 #endif
 #ifndef EUCL_SHADE_LIGHT_MIN_BLOCKS
 #define EUCL_SHADE_LIGHT_MIN_BLOCKS 2 /* 3d_room 4K, shade ms per frame: 3 CTAs of 256 (80 registers, 370 B of spills) 8.50; 5 of 128 (96) 8.03; 4 of 128 / 2 of 256 (128 registers, no spills) 7.29 / 7.16 */
