@@ -313,7 +313,11 @@ uint32_t eucl_band_rows_for_rank(const EuclRenderOpts* opts);
  * Synchronous.  out_hit_ids and stats may be NULL.
  * Band-split renders (band_world > 1) with compact_rows == 0 write ONLY this rank's rows of the full-frame
  * buffer and touch nothing else: N processes, one per GPU, may pass the same shared (ideally pinned) host
- * frame and fill it over their own PCIe links at the same time. */
+ * frame and fill it over their own PCIe links at the same time.
+ * Frames of 65536 pixels or more are rendered as two pipelines side by side (every other 16-row band each; EUCL_SPLIT=1
+ * turns that off): the scene then owns a helper host thread and a second set of CUDA streams; both are created at the
+ * first such frame, ordered after / joined into the scene's stream around every call, and released by eucl_scene_destroy.
+ * EuclStats of such a frame are the sums over the pipelines (ms_total: first launch to last completion). */
 int eucl_render(EuclScene* scene, const EuclCamera* camera, const EuclRenderOpts* opts,
                 uint8_t* out_rgb8, int32_t* out_hit_ids, EuclStats* stats);
 
