@@ -55,3 +55,21 @@ def test_committed_launch_list_matches_its_summary():
             family = ln.split("<")[0].split()[0]
             shares[family] = shares.get(family, 0.0) + float(ln.split("share=")[1].rstrip("%"))
     assert 40 < shares["k_intersect"] < 48 and 42 < shares["k_shade"] < 50 and shares["k_resolve"] + shares["k_final"] < 12
+
+
+def test_split_launch_list_matches_its_summary():
+    """The launch list of the final build: two pipelines per frame interleave in it (two k_raygen ... two k_final)."""
+    csv = ROOT / "profiles" / "r2_launches_bench_3d_room_4k_split.csv"
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "launch_summary.py"), str(csv), "--warmup", "8", "--steps", "2"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    committed = (ROOT / "profiles" / "r2_launches_bench_3d_room_4k_split_summary.txt").read_text().splitlines()
+    assert r.stdout.splitlines() == [ln for ln in committed if not ln.startswith("# EUCL_GRAPH=0")]
+    counts, shares = {}, {}
+    for ln in r.stdout.splitlines():
+        if "share=" in ln:
+            family = ln.split("<")[0].split()[0]
+            counts[family] = counts.get(family, 0) + int(ln.split("n=")[1].split()[0])
+            shares[family] = shares.get(family, 0.0) + float(ln.split("share=")[1].rstrip("%"))
+    assert counts["k_raygen"] == 4 and counts["k_final"] == 4  # 2 frames x 2 pipelines
+    assert 40 < shares["k_intersect"] < 50 and 42 < shares["k_shade"] < 52 and shares["k_resolve"] + shares["k_final"] < 8
